@@ -1,0 +1,73 @@
+/* TEST INFRASTRUCTURE -- not part of the product path.
+ *
+ * Batch driver linked next to an instantiated reference solver (oracle/instantiate.py).
+ * It only loops over instances and calls the reference's single-instance function with the
+ * reference's own signature (e.g. header_laxMPC_FISTA_C.h:26); it contains no solver arithmetic.
+ * Optional pthreads split the batch in contiguous slices (one per thread) for the all-cores
+ * CPU baseline of SURVEY.md section 8(d).
+ *
+ * Compile-time parameters (set by instantiate.py):
+ *   SPCIES_HDR   "<save_name>.h"      generated header (defines nn_, mm_, ... and sol_<save_name>)
+ *   SPCIES_FUNC  e.g. laxMPC_FISTA    the reference solver symbol
+ *   SPCIES_SOL   sol_<save_name>
+ *   SPCIES_HAS_R 0|1                  1 for ellipMPC_ADMM_soc (extra double *r_ellip input)
+ */
+#include SPCIES_HDR
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef struct {
+    long lo, hi;
+    const double *x0, *xr, *ur, *r;
+    double *u, *sol;
+    int *k, *e;
+} slice_t;
+
+long spcies_ref_sol_doubles(void) { return (long)(sizeof(SPCIES_SOL) / sizeof(double)); }
+
+static void *run_slice(void *arg) {
+    slice_t *s = (slice_t *)arg;
+    const long nsol = spcies_ref_sol_doubles();
+    SPCIES_SOL sol;
+    double x0[nn_], xr[nn_], ur[mm_], u[mm_];
+    for (long i = s->lo; i < s->hi; i++) {
+        int k = 0, e = 0;
+        memcpy(x0, s->x0 + i * nn_, sizeof x0);
+        memcpy(xr, s->xr + i * nn_, sizeof xr);
+        memcpy(ur, s->ur + i * mm_, sizeof ur);
+        memset(&sol, 0, sizeof sol);
+#if SPCIES_HAS_R
+        double r = s->r[i];
+        SPCIES_FUNC(x0, xr, ur, &r, u, &k, &e, &sol);
+#else
+        SPCIES_FUNC(x0, xr, ur, u, &k, &e, &sol);
+#endif
+        memcpy(s->u + i * mm_, u, sizeof u);
+        s->k[i] = k;
+        s->e[i] = e;
+        if (s->sol) memcpy(s->sol + i * nsol, &sol, sizeof sol);
+    }
+    return NULL;
+}
+
+int spcies_ref_batch(long B, const double *x0, const double *xr, const double *ur, const double *r,
+                     double *u, int *k, int *e, double *sol, int nthreads) {
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > 256) nthreads = 256;
+    if ((long)nthreads > B) nthreads = B > 0 ? (int)B : 1;
+    pthread_t th[256];
+    slice_t sl[256];
+    long per = (B + nthreads - 1) / nthreads;
+    for (int t = 0; t < nthreads; t++) {
+        long lo = t * per, hi = lo + per;
+        if (lo > B) lo = B;
+        if (hi > B) hi = B;
+        sl[t] = (slice_t){lo, hi, x0, xr, ur, r, u, sol, k, e};
+    }
+    if (nthreads == 1) { run_slice(&sl[0]); return 0; }
+    for (int t = 0; t < nthreads; t++)
+        if (pthread_create(&th[t], NULL, run_slice, &sl[t]) != 0) return -1;
+    for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
+    return 0;
+}

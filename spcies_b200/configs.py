@@ -1,0 +1,84 @@
+"""Named problem configurations.
+
+* ``reference_test(name)``: the settings of the reference's own ``tests/test_<name>.m``
+  (3-mass system of tests/spcies_tester.m:90-116, ``tol = 1e-7``, ``k_max = 5000``).
+* ``bench_config(name)``: configurations C1..C5 of BASELINE.json / SURVEY.md section 8(d).
+
+Each returns ``dict(sys=..., param=..., kw=...)`` where ``kw`` are the name-value arguments of
+``spcies_gen_controller`` (formulation, method, submethod, options).
+"""
+from __future__ import annotations
+
+import numpy as np
+import scipy.linalg as sla
+
+from . import sysmodel
+
+
+def _QR(sys):
+    p = sys['p']
+    return sla.block_diag(15.0 * np.eye(p), np.eye(p)), 0.1 * np.eye(sys['m'])
+
+
+def _T_sumP(sys, Q, R):
+    """``[~, T] = dlqr(A,B,Q,R); T = diag(sum(T, 2))`` (tests/test_laxMPC_FISTA.m:13-14)."""
+    _, P = sysmodel.dlqr(sys['A'], sys['B'], Q, R)
+    return np.diag(P.sum(axis=1))
+
+
+def reference_test(name: str, N: int = 10, **solver_overrides):
+    sys = sysmodel.oscillating_masses_sys()
+    Q, R = _QR(sys)
+    st = sysmodel.tester_status(sys)
+    if name in ('laxMPC_FISTA', 'laxMPC_ADMM'):
+        param = dict(Q=Q, R=R, T=_T_sumP(sys, Q, R), N=N)
+        so = dict(k_max=5000, tol=1e-7) if name.endswith('FISTA') else dict(rho=15.0, k_max=5000, tol=1e-7)
+        kw = dict(formulation='laxMPC', method=name.split('_')[1])
+    elif name in ('equMPC_FISTA', 'equMPC_ADMM'):
+        param = dict(Q=Q, R=R, N=N)
+        so = dict(k_max=5000, tol=1e-7) if name.endswith('FISTA') else dict(rho=15.0, k_max=5000, tol=1e-7)
+        kw = dict(formulation='equMPC', method=name.split('_')[1])
+    elif name == 'ellipMPC_ADMM':
+        param = dict(Q=Q, R=R, T=_T_sumP(sys, Q, R), N=N, P=np.eye(sys['n']), c=st['xr'], r=0.0)
+        so = dict(rho=15.0, k_max=5000, tol=1e-7)
+        kw = dict(formulation='ellipMPC', method='ADMM')
+    elif name == 'ellipMPC_ADMM_soc':
+        param = dict(Q=Q, R=R, T=_T_sumP(sys, Q, R), N=N, P=np.eye(sys['n']), c=st['xr'], r=0.0)
+        so = dict(rho=15.0, sigma=10.0, k_max=5000, tol_p=1e-7, tol_d=1e-7)
+        kw = dict(formulation='ellipMPC', method='ADMM', submethod='soc')
+    elif name == 'MPCT_EADMM':
+        param = dict(Q=Q, R=R, T=10.0 * Q, S=R, N=N)
+        so = dict(rho_base=2.0, rho_mult=20.0, k_max=5000, tol=1e-7)
+        kw = dict(formulation='MPCT', method='EADMM')
+    elif name in ('HMPC_ADMM_split', 'HMPC_SADMM_split'):
+        param = dict(Q=Q, R=R, N=N, w=3 * 1.627 * 0.2, Te=10.0 * N * Q, Se=R)
+        param['Th'] = param['Te']
+        param['Sh'] = 0.5 * param['Se']
+        so = dict(rho=2.0, sigma=20.0, k_max=5000, tol_p=1e-7, tol_d=1e-7, use_soc=False)
+        kw = dict(formulation='HMPC', method='SADMM' if 'SADMM' in name else 'ADMM', submethod='split')
+    else:
+        raise KeyError(name)
+    so.update(debug=True, timing=False)
+    so.update(solver_overrides)
+    kw['options'] = so
+    return dict(sys=sys, param=param, kw=kw, status=st, name=name)
+
+
+def bench_config(name: str):
+    """C1/C2: laxMPC FISTA N=10 defaults; C3: equMPC ADMM N=20 rho=15; C4: ellipMPC ADMM_soc N=10;
+    C5a: HMPC SADMM_split N=50; C5b: MPCT EADMM N=50."""
+    table = {
+        'C1': ('laxMPC_FISTA', 10, dict(tol=1e-4, k_max=1000)),
+        'C2': ('laxMPC_FISTA', 10, dict(tol=1e-4, k_max=1000)),
+        'C3': ('equMPC_ADMM', 20, dict(rho=15.0, tol=1e-4, k_max=1000)),
+        'C3f': ('equMPC_ADMM', 20, dict(rho=15.0, tol=1e-4, k_max=1000, precision='float')),
+        'C4': ('ellipMPC_ADMM_soc', 10, dict(rho=15.0, sigma=10.0, tol_p=1e-4, tol_d=1e-4, k_max=1000)),
+        'C5a': ('HMPC_SADMM_split', 50, dict(rho=2.0, sigma=20.0, alpha=0.95, tol_p=1e-4, tol_d=1e-4, k_max=1000)),
+        'C5b': ('MPCT_EADMM', 50, dict(rho_base=2.0, rho_mult=20.0, tol=1e-4, k_max=1000)),
+    }
+    solver, N, so = table[name]
+    cfg = reference_test(solver, N=N, **so)
+    cfg['kw']['options'].update(debug=False)
+    cfg['name'] = name
+    cfg['solver'] = solver
+    return cfg

@@ -1,0 +1,197 @@
+"""HMPC (harmonic MPC) -- ADMM_split / SADMM_split recipes.
+
+Host-side restatement of formulations/+HMPC/compute_HMPC_ADMM_split_ingredients.m:23-325
+and cons_HMPC_ADMM_split_C.m:43-162 (cons_HMPC_SADMM_split_C.m:45 delegates to it; SADMM
+only adds the ``alpha_SADMM`` / ``IS_SYMMETRIC`` defines).
+
+Known reference defects handled here:
+* cons_HMPC_ADMM_split_C.m:95 reads a non-existent ``recipe.solver_options``; the intent
+  (``recipe.options.solver.box_constraints``) is used.
+* the sparse (``sparse=true``) path relies on MATLAB ``ldl`` with pivoting; only the
+  default dense path (``NON_SPARSE``: ``M1``, ``M2``) is generated.
+"""
+from __future__ import annotations
+
+import numpy as np
+import scipy.linalg as sla
+
+from .common import (Row, SolverSpec, default_defines, dynamics_constraint, engineering_rows,
+                     get_sys_param, scaling_vars, var_options)
+
+
+def compute_HMPC_ADMM_split_ingredients(recipe, box_constraints=True):
+    A, B, n, m, N = get_sys_param(recipe)
+    sys, param, solver = recipe.sys, recipe.param, recipe.options.solver
+    nm = n + m
+    LBx, UBx = np.asarray(sys['LBx'], float).ravel(), np.asarray(sys['UBx'], float).ravel()
+    LBu, UBu = np.asarray(sys['LBu'], float).ravel(), np.asarray(sys['UBu'], float).ravel()
+    if not box_constraints:
+        E, F = np.asarray(sys['E'], float), np.asarray(sys['F'], float)
+        LBy, UBy = np.asarray(sys['LBy'], float).ravel(), np.asarray(sys['UBy'], float).ravel()
+    else:
+        E = np.vstack([np.eye(n), np.zeros((m, n))])
+        F = np.vstack([np.zeros((n, m)), np.eye(m)])
+        LBy, UBy = np.concatenate([LBx, LBu]), np.concatenate([UBx, UBu])
+    n_y = LBy.size
+    w = float(param['w'])
+    Q, R, Te, Th, Se, Sh = (np.asarray(param[k], float) for k in ('Q', 'R', 'Te', 'Th', 'Se', 'Sh'))
+    use_soc = bool(solver.get('use_soc', False))
+
+    js = np.arange(N)
+    s_j, c_j = np.sin(w * js), np.cos(w * js)
+    # accumulate in the reference's order (:84-95) so the sums match to the last bit
+    s_sum = c_sum = s2_sum = c2_sum = sc_sum = 0.0
+    for j in range(N):
+        s_sum += np.sin(w * j)
+        c_sum += np.cos(w * j)
+        s2_sum += np.sin(w * j) ** 2
+        c2_sum += np.cos(w * j) ** 2
+        sc_sum += np.sin(w * j) * np.cos(w * j)
+
+    H11 = sla.block_diag(R, np.kron(np.eye(N - 1), sla.block_diag(Q, R)))
+    H12 = np.zeros(((N - 1) * nm + m, 3 * n))
+    for j in range(N - 1):
+        H12[j * nm + m:(j + 1) * nm, :] = np.kron([[1.0, s_j[j + 1], c_j[j + 1]]], -Q)
+    H13 = np.zeros(((N - 1) * nm + m, 3 * m))
+    for j in range(N):
+        H13[j * nm:j * nm + m, :] = np.kron([[1.0, s_j[j], c_j[j]]], -R)
+    H22 = np.block([[Te + N * Q, s_sum * Q, c_sum * Q],
+                    [s_sum * Q, Th + s2_sum * Q, sc_sum * Q],
+                    [c_sum * Q, sc_sum * Q, Th + c2_sum * Q]])
+    H33 = np.block([[Se + N * R, s_sum * R, c_sum * R],
+                    [s_sum * R, Sh + s2_sum * R, sc_sum * R],
+                    [c_sum * R, sc_sum * R, Sh + c2_sum * R]])
+    H23 = np.zeros((3 * n, 3 * m))
+    H = np.block([[H11, H12, H13], [H12.T, H22, H23], [H13.T, H23.T, H33]])
+    dim = H.shape[0]
+
+    G = dynamics_constraint(A, B, N, n_identities=N - 2)
+    In = np.eye(n)
+    G = np.hstack([G, np.vstack([np.zeros((G.shape[0] - n, 3 * nm)),
+                                 np.hstack([-In, -In * np.sin(w * N), -In * np.cos(w * N), np.zeros((n, 3 * m))])])])
+    Zn, Znm = np.zeros((n, n)), np.zeros((n, m))
+    harm = np.block([[A - In, Zn, Zn, B, Znm, Znm],
+                     [Zn, A - np.cos(w) * In, np.sin(w) * In, Znm, B, Znm],
+                     [Zn, -np.sin(w) * In, A - np.cos(w) * In, Znm, Znm, B]])
+    G = np.vstack([G, np.hstack([np.zeros((3 * n, G.shape[1] - 3 * nm)), harm])])
+    n_eq = G.shape[0]
+    b = np.zeros(n * (N + 3))
+
+    def soc_blocks():
+        C_aux, dsoc = [], []
+        for j in range(n_y):
+            Ej, Fj = E[j:j + 1, :], F[j:j + 1, :]
+            Eub, Elb = sla.block_diag(Ej, -Ej, -Ej), sla.block_diag(-Ej, -Ej, -Ej)
+            Fub, Flb = sla.block_diag(Fj, -Fj, -Fj), sla.block_diag(-Fj, -Fj, -Fj)
+            C_aux.append(np.vstack([np.hstack([Eub, Fub]), np.hstack([Elb, Flb])]))
+            dsoc += [UBy[j], 0.0, 0.0, -LBy[j], 0.0, 0.0]
+        return np.vstack(C_aux), np.array(dsoc), 2 * n_y
+
+    if not box_constraints:
+        if use_soc:
+            C_aux, dsoc, n_soc = soc_blocks()
+        else:
+            C_aux = np.vstack([np.hstack([np.kron(np.eye(3), -E[j:j + 1, :]), np.kron(np.eye(3), -F[j:j + 1, :])])
+                               for j in range(n_y)])
+            dsoc, n_soc = np.zeros(3 * n_y), n_y
+        C = sla.block_diag(-F, np.kron(np.eye(N - 1), np.hstack([-E, -F])), C_aux)
+        d = np.concatenate([np.zeros(N * n_y), dsoc])
+    else:
+        if use_soc:
+            C_aux, dsoc, n_soc = soc_blocks()
+        else:
+            C_n = np.vstack([np.kron(np.eye(3), -np.eye(n)[j:j + 1, :]) for j in range(n)])
+            C_m = np.vstack([np.kron(np.eye(3), -np.eye(m)[j:j + 1, :]) for j in range(m)])
+            C_aux = sla.block_diag(C_n, C_m)
+            dsoc, n_soc = np.zeros(3 * n_y), n_y
+        C = np.hstack([np.zeros((3 * n_soc, dim - 3 * nm)), C_aux])
+        d = dsoc
+    n_s = C.shape[0]
+
+    sigma, rho = float(solver['sigma']), float(solver['rho'])
+    Hh = sla.block_diag(H + sigma * np.eye(dim), rho * np.eye(n_s))
+    Gh = np.block([[G, np.zeros((n_eq, n_s))], [C, np.eye(n_s)]])
+    bh = np.concatenate([b, d])
+    Hhi = np.linalg.inv(Hh)
+    W = Gh @ Hhi @ Gh.T
+    Wi = np.linalg.inv(W)
+    M1 = Hhi @ Gh.T @ Wi @ Gh @ Hhi - Hhi
+    M2 = Hhi @ Gh.T @ Wi
+
+    v = dict(dim=dim, n_s=n_s, n_eq=n_eq, N=N, n=n, m=m, n_y=n_y, n_soc=n_soc,
+             Q=Q, Te=Te, Se=Se, A=A,
+             LB=np.concatenate([LBu, np.kron(np.ones(N - 1), np.concatenate([LBx, LBu]))]),
+             UB=np.concatenate([UBu, np.kron(np.ones(N - 1), np.concatenate([UBx, UBu]))]),
+             LBy=LBy, UBy=UBy, E=E, F=F, H=H, Hh=Hh, G=G, b=b, C=C, d=d, Gh=Gh, bh=bh,
+             M1=M1, M2=M2, rho=rho, rho_i=1.0 / rho, sigma=sigma, sigma_i=1.0 / sigma,
+             k_max=int(solver['k_max']), tol_p=float(solver['tol_p']), tol_d=float(solver['tol_d']),
+             use_soc=use_soc, box_constraints=box_constraints, w=w)
+    v.update(scaling_vars(sys, n, m))
+    return v
+
+
+def _cons_split(recipe, symmetric: bool) -> SolverSpec:
+    opts = recipe.options
+    solver = opts.solver
+    box = solver.get('box_constraints', None)
+    if box is None or (isinstance(box, (list, tuple)) and len(box) == 0):
+        box = 'E' not in recipe.sys                     # cons_HMPC_ADMM_split_C.m:56-62
+    box = bool(box)
+    if solver.get('sparse', False):
+        raise NotImplementedError(
+            "HMPC split solver with sparse=true needs MATLAB's pivoted ldl (compute_HMPC_ADMM_split_ingredients.m:228-233); "
+            "only the default dense (NON_SPARSE) path is generated")
+    v = compute_HMPC_ADMM_split_ingredients(recipe, box)
+    n, m, N, dim, n_s, n_eq = v['n'], v['m'], v['N'], v['dim'], v['n_s'], v['n_eq']
+    vopt = var_options(opts)
+    vopt_pen = var_options(opts, array=False)
+    prec = opts.precision
+    D = ('define',)
+    defs = default_defines(opts)
+    defs += [Row('nn_', n, True, 'uint', D), Row('mm_', m, True, 'uint', D), Row('nm_', n + m, True, 'uint', D)]
+    if not box:
+        defs.append(Row('n_y', v['n_y'], True, 'uint', D))
+    defs += [Row('NN_', N, True, 'uint', D), Row('dim', dim, True, 'uint', D), Row('n_s', n_s, True, 'uint', D),
+             Row('n_eq', n_eq, True, 'uint', D), Row('n_soc', v['n_soc'], True, 'uint', D),
+             Row('NON_SPARSE', 1, True, 'bool', D)]
+    if not box:
+        defs.append(Row('COUPLED_CONSTRAINTS', 1, True, 'bool', D))
+    defs += [Row('k_max', int(solver['k_max']), True, 'uint', D),
+             Row('tol_p', float(solver['tol_p']), True, prec, D),
+             Row('tol_d', float(solver['tol_d']), True, prec, D)]
+    if symmetric:
+        defs += [Row('alpha_SADMM', float(solver['alpha']), True, prec, D),
+                 Row('IS_SYMMETRIC', 1, True, prec, D)]
+    if v['use_soc']:
+        defs.append(Row('USE_SOC', 1, True, prec, D))
+    consts = [Row(k, v[k], True, prec, vopt_pen) for k in ('rho', 'rho_i', 'sigma', 'sigma_i')]
+    consts += [Row('A', v['A'], True, prec, vopt), Row('QQ', v['Q'], True, prec, vopt),
+               Row('Te', v['Te'], True, prec, vopt), Row('Se', v['Se'], True, prec, vopt),
+               Row('LB', v['LB'], True, prec, vopt), Row('UB', v['UB'], True, prec, vopt),
+               Row('LBy', v['LBy'], True, prec, vopt), Row('UBy', v['UBy'], True, prec, vopt),
+               Row('M1', v['M1'], True, prec, vopt)]
+    if v['use_soc']:
+        consts.append(Row('M2', v['M2'], True, prec, vopt))
+        defs.append(Row('dim_M2', n_eq + n_s, True, prec, D))
+    else:
+        consts.append(Row('M2', v['M2'][:, :n].copy(), True, prec, vopt))
+        defs.append(Row('dim_M2', n, True, prec, D))
+    if opts.in_engineering:
+        consts += engineering_rows(v, prec, vopt)
+    variables = [Row('bh', v['bh'], True, prec, ())]
+    method = 'SADMM' if symmetric else 'ADMM'
+    return SolverSpec(
+        formulation='HMPC', method=method, submethod='split', func_name='HMPC_ADMM', kernel='HMPC_ADMM_split',
+        defines=defs, constants=consts, variables=variables,
+        ref_code='formulations/+HMPC/code_HMPC_ADMM_split_C.c',
+        ref_header='formulations/+HMPC/header_HMPC_ADMM_split_C.h',
+        sol_fields=(('z', dim), ('s', n_s), ('z_hat', dim), ('s_hat', n_s), ('lambda', dim), ('mu', n_s)),
+        vars=v, dims=dict(n=n, m=m, N=N, dim=dim, n_s=n_s, n_eq=n_eq))
+
+
+def cons_HMPC_ADMM_split(recipe):
+    return _cons_split(recipe, False)
+
+
+def cons_HMPC_SADMM_split(recipe):
+    return _cons_split(recipe, True)

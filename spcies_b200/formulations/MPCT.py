@@ -1,0 +1,145 @@
+"""MPCT (MPC for tracking with artificial reference) -- EADMM recipe.
+
+Host-side restatement of formulations/+MPCT/compute_MPCT_EADMM_ingredients.m:21-316
+and cons_MPCT_EADMM_C.m.
+"""
+from __future__ import annotations
+
+import numpy as np
+import scipy.linalg as sla
+
+from .common import (Row, SolverSpec, alpha_beta_from_chol, chol_upper, default_defines,
+                     engineering_rows, get_sys_param, isdiag, scaling_vars, var_options)
+
+
+def compute_MPCT_EADMM_ingredients(recipe):
+    A, B, n, m, N = get_sys_param(recipe)
+    sys, param, opt = recipe.sys, recipe.param, recipe.options
+    nm = n + m
+    Q, R, T, S = (np.asarray(param[k], float) for k in ('Q', 'R', 'T', 'S'))
+    inf = float(opt.inf_value)
+    LBx = np.asarray(sys.get('LBx', -inf * np.ones(n)), float).ravel()
+    UBx = np.asarray(sys.get('UBx', inf * np.ones(n)), float).ravel()
+    LBu = np.asarray(sys.get('LBu', -inf * np.ones(m)), float).ravel()
+    UBu = np.asarray(sys.get('UBu', inf * np.ones(m)), float).ravel()
+
+    solver = opt.solver
+    if 'rho' in solver:                         # compute_MPCT_EADMM_ingredients.m:70-73
+        rho_base, rho_mult = float(solver['rho']), 1.0
+    else:
+        rho_base, rho_mult = float(solver['rho_base']), float(solver['rho_mult'])
+
+    # Penalty vector; MATLAB end-relative slices restated 0-based
+    L = (N + 1) * nm + n + nm
+    rho = rho_base * np.ones(L)
+    big = rho_mult * rho_base
+    rho[0:n] = big                              # x_0 = x                      (6b)
+    rho[n:2 * n] = big                          # initial z1 + z2 + z3 = 0     (6i), i = 0
+    rho[L - 2 * nm:L - nm - m] = big            # final   z1 + z2 + z3 = 0     (6i), i = N
+    rho[L - nm:L - m] = big                     # x_N = x_s                    (6k)
+    rho[L - 2 * nm + n:L - nm] = big            # final   z1 + z2 + z3 = 0     (6j), i = N
+    rho[L - m:L] = big                          # u_N = u_s                    (6l)
+
+    A1 = -np.vstack([np.hstack([-np.eye(n), np.zeros((n, N * nm + m))]),
+                     np.eye((N + 1) * nm),
+                     np.hstack([np.zeros((nm, N * nm)), np.eye(nm)])])
+    A2 = np.vstack([np.zeros((n, nm)), np.kron(np.ones((N, 1)), np.eye(nm)),
+                    np.kron(np.ones((2, 1)), np.eye(nm))])
+    A3 = np.vstack([np.zeros((n, (N + 1) * nm)), np.eye((N + 1) * nm), np.zeros((nm, (N + 1) * nm))])
+
+    rA1 = rho[:, None] * A1                     # ``rho.*A`` scales rows
+    H1 = rA1.T @ A1
+    H1i = 1.0 / np.diag(H1)
+
+    H2 = sla.block_diag(T, S) + (rho[:, None] * A2).T @ A2
+    Az2 = np.hstack([A - np.eye(n), B])
+    H2i = np.linalg.inv(H2)
+    W2 = H2i @ Az2.T @ np.linalg.inv(Az2 @ H2i @ Az2.T) @ Az2 @ H2i - H2i
+
+    H3 = np.kron(np.eye(N + 1), sla.block_diag(Q, R)) + (rho[:, None] * A3).T @ A3
+    Az3 = np.kron(np.eye(N), np.hstack([A, B]))
+    for j in range(N - 1):                      # -I blocks, no growth here (Az3 is N blocks wide)
+        c0 = j * nm + nm
+        Az3[j * n:(j + 1) * n, c0:c0 + n] = -np.eye(n)
+    Az3 = np.hstack([Az3, np.vstack([np.zeros(((N - 1) * n, n)), -np.eye(n)]), np.zeros((N * n, m))])
+    H3inv = np.linalg.inv(H3)
+    W3 = Az3 @ H3inv @ Az3.T
+    W3c = chol_upper(W3)
+
+    diag_ok = bool(opt.force_diagonal) and isdiag(Q) and isdiag(R)
+
+    v = dict(n=n, m=m, N=N, force_diagonal=diag_ok)
+    v['H1i'] = H1i.reshape(N + 1, nm).copy()
+    if diag_ok:
+        v['H3i'] = (1.0 / np.diag(H3)).reshape(N + 1, nm).copy()
+    else:
+        Qm = np.linalg.inv(Q + big * np.eye(n))
+        Rm = np.linalg.inv(R + big * np.eye(m))
+        Qb = np.linalg.inv(Q + rho_base * np.eye(n))
+        Rb = np.linalg.inv(R + rho_base * np.eye(m))
+        v.update(Q_mult_inv=Qm, Q_base_inv=Qb, R_mult_inv=Rm, R_base_inv=Rb,
+                 AB_base_inv=np.hstack([A, B]) @ sla.block_diag(Qb, Rb),
+                 AB_mult_inv=np.hstack([A, B]) @ sla.block_diag(Qm, Rb))
+    v['AB'] = np.hstack([A, B])
+    v['W2'] = W2
+    v['T'] = -T
+    v['S'] = -S
+
+    def clipinf(x, s):
+        x = np.array(x, float)
+        x[np.isinf(x)] = s * inf
+        return x
+    eps_x, eps_u = float(solver['epsilon_x']), float(solver['epsilon_u'])
+    v['LB'] = clipinf(np.concatenate([LBx, LBu]), -1)
+    v['UB'] = clipinf(np.concatenate([UBx, UBu]), +1)
+    v['LBs'] = clipinf(np.concatenate([LBx + eps_x, LBu + eps_u]), -1)
+    v['UBs'] = clipinf(np.concatenate([UBx - eps_x, UBu - eps_u]), +1)
+    v['LB0'] = np.concatenate([-inf * np.ones(n), LBu])
+    v['UB0'] = np.concatenate([inf * np.ones(n), UBu])
+    v['rho'] = rho[n:L - nm].reshape(N + 1, nm).copy()
+    v['rho_0'] = np.concatenate([rho[:n], np.zeros(m)])
+    v['rho_s'] = rho[L - nm:].copy()
+    v['Alpha'], v['Beta'] = alpha_beta_from_chol(W3c, n, N)
+    v.update(scaling_vars(sys, n, m))
+    # dense pieces for the non-sparse twin (vars_nonsparse in the reference)
+    v['dense'] = dict(A1=A1, A2=A2, A3=A3, rho=rho, H1i=H1i, T=T, S=S, W2=W2, H3inv=H3inv, Az3=Az3, W3=W3,
+                      LB=np.concatenate([v['LB0'], np.kron(np.ones(N - 1), v['LB']), v['LBs']]),
+                      UB=np.concatenate([v['UB0'], np.kron(np.ones(N - 1), v['UB']), v['UBs']]))
+    return v
+
+
+def cons_MPCT_EADMM(recipe) -> SolverSpec:
+    opts = recipe.options
+    v = compute_MPCT_EADMM_ingredients(recipe)
+    # cons_MPCT_EADMM_C.m: force_diagonal follows whether H3i exists *before* the default #defines are built
+    opts = opts.copy()
+    opts.force_diagonal = bool(v['force_diagonal'])
+    n, m, N = v['n'], v['m'], v['N']
+    vopt = var_options(opts)
+    prec = opts.precision
+    D = ('define',)
+    defs = default_defines(opts)
+    defs += [Row('nn_', n, True, 'uint', D), Row('mm_', m, True, 'uint', D),
+             Row('nm_', n + m, True, 'uint', D), Row('NN_', N, True, 'uint', D),
+             Row('k_max', int(opts.solver['k_max']), True, 'uint', D),
+             Row('tol', float(opts.solver['tol']), True, 'float', D)]
+    names = [('rho', 'rho'), ('rho_0', 'rho_0'), ('rho_s', 'rho_s'), ('LB', 'LB'), ('UB', 'UB'),
+             ('LB_0', 'LB0'), ('UB_0', 'UB0'), ('LB_s', 'LBs'), ('UB_s', 'UBs'), ('AB', 'AB'),
+             ('T', 'T'), ('S', 'S'), ('Alpha', 'Alpha'), ('Beta', 'Beta'), ('H1i', 'H1i'), ('W2', 'W2')]
+    consts = [Row(cn, v[vn], True, prec, vopt) for cn, vn in names]
+    if opts.force_diagonal:
+        consts.append(Row('H3i', v['H3i'], True, prec, vopt))
+    else:
+        consts += [Row('Q_bi', v['Q_base_inv'], True, prec, vopt), Row('Q_mi', v['Q_mult_inv'], True, prec, vopt),
+                   Row('R_bi', v['R_base_inv'], True, prec, vopt), Row('R_mi', v['R_mult_inv'], True, prec, vopt),
+                   Row('AB_bi', v['AB_base_inv'], True, prec, vopt), Row('AB_mi', v['AB_mult_inv'], True, prec, vopt)]
+    if opts.in_engineering:
+        consts += engineering_rows(v, prec, vopt)
+    nm = n + m
+    return SolverSpec(
+        formulation='MPCT', method='EADMM', submethod='', func_name='MPCT_EADMM', kernel='MPCT_EADMM',
+        defines=defs, constants=consts,
+        ref_code='formulations/+MPCT/code_MPCT_EADMM_C.c',
+        ref_header='formulations/+MPCT/header_MPCT_EADMM_C.h',
+        sol_fields=(('z1', (N + 1) * nm), ('z2', nm), ('z3', (N + 1) * nm), ('lambda', (N + 3) * nm)),
+        vars=v, dims=dict(n=n, m=m, N=N))

@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py -- batched MPC QP solves/s on B200 (BASELINE.json metric), one JSON line.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config C2] [--impl reference]
+
+A *step* is one pass of the hot path over one batch of synthetic instances (SURVEY.md 8(d) generator).
+N = 1 workload: configs[1] of BASELINE.json -- laxMPC FISTA, oscillating masses N=10, B = 1,048,576 random
+x0 / references.  N > 1 (torchrun, one rank per GPU): every rank solves its own 1 Mi-instance shard, no
+collective on the data path (weak scaling); the time is the max over ranks.
+
+value      whole-job solves/s with inputs resident in HBM (device-pointer entry of the C ABI, kernel +
+           its launch overhead), timed with CUDA events on the launching stream.
+e2e        same metric through the host-buffer C-ABI call (pinned host arrays; H2D and D2H inside the
+           timed region) -- the headline against `--impl reference`.
+roofline   dominant kernel (the persistent solver kernel; it is the only kernel of a step):
+           algorithmic FP64 flops / launch duration vs the FP64 FMA ceiling measured by
+           spcies_b200/csrc/microbench.cu in the same run (MEASURED_PEAKS.json has no FP64 figure;
+           its HBM number bounds the batch I/O, reported in roofline.hbm).
+cpu_baseline  the instantiated reference C solver (oracle/_ref, gcc -O3) on this box's host cores,
+           bounded sample of the same batch.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # config -> (prebuilt solver, per-GPU batch, description)
+    'C2': ('C2_laxMPC_FISTA', 1 << 20, 'laxMPC FISTA oscillating masses N=10, 1Mi random x0/references per GPU'),
+}
+
+
+def fma_per_instance(solver_name, dims, sum_k, B):
+    """Algorithmic FMA count: laxMPC FISTA  FMA(k) = (k+1) F_zr + k F_W."""
+    n, m, N = dims['n'], dims['m'], dims['N']
+    nm = n + m
+    if solver_name == 'laxMPC_FISTA':
+        F_zr = 2 * (m * n + (N - 1) * n * nm)
+        F_W = 2 * (N * n * (n - 1) // 2 + (N - 1) * n * n)
+        return (sum_k + B) * F_zr + sum_k * F_W
+    raise KeyError(solver_name)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nme, val in zip(names, f[3:7]):
+                if val.lower().startswith('active'):
+                    reasons.add(nme)
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no samples']}
+        return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(mx)), 'reasons': sorted(reasons),
+                'power_w_max': float(max(pw)), 'samples': len(sm)}
+
+
+def run_microbench():
+    exe = os.path.join(ROOT, 'generated_solvers', 'spcies_microbench')
+    if not os.path.exists(exe):
+        return None
+    try:
+        out = subprocess.run([exe], capture_output=True, text=True, timeout=120).stdout.strip().splitlines()[-1]
+        return json.loads(out)
+    except Exception as ex:                                    # pragma: no cover
+        return {'error': str(ex)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        return json.load(open(p)), 'measured'
+    return {'hbm_gbs': 6650.0}, 'fallback'
+
+
+def cpu_reference_leg(save_name, batch, sample, threads):
+    """Time the instantiated reference C solver (oracle/_ref) on a bounded sample.  Checker / baseline only."""
+    from oracle import refs
+    ref = refs.get(save_name)[0]
+    x0, xr, ur = batch['x0'][:sample], batch['xr'][:sample], batch['ur'][:sample]
+    ref.solve_batch(x0[:256], xr[:256], ur[:256], threads=1)            # warm the code path
+    t0 = time.perf_counter()
+    u, k, e = ref.solve_batch(x0, xr, ur, threads=threads)
+    dt = time.perf_counter() - t0
+    return sample / dt, dt, u, k, e
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--config', default='C2')
+    ap.add_argument('--impl', default='native', choices=['native', 'reference'])
+    ap.add_argument('--batch', type=int, default=0, help='override the per-GPU batch (testing only)')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    save_name, B, desc = WORKLOADS[args.config]
+    if args.batch:
+        B = args.batch
+    W = max(args.warmup, 3)
+    K = max(args.steps, 1)
+
+    from spcies_b200 import prebuilt, sysmodel
+    spec, cfg = prebuilt.spec_for(save_name)
+    dims = spec.dims
+    metric = 'batched MPC QP solves/sec'
+    config = {'workload': desc, 'solver': spec.options.solver_key(), 'formulation': spec.formulation,
+              'method': spec.method, 'N': dims['N'], 'nn': dims['n'], 'mm': dims['m'],
+              'batch_per_gpu': B, 'tol': spec.define('tol'), 'k_max': spec.define('k_max'),
+              'arith': 'fast (FMA)', 'l2': 'inputs larger than L2: 3 distinct batches rotated between steps',
+              'seed': 'numpy default_rng(100 + 3*rank + i)'}
+
+    # ---------------------------------------------------------------- reference arm (CPU)
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        cores = os.cpu_count() or 1
+        sample = min(B, 1 << 17)
+        batch = sysmodel.synthetic_batch(cfg['sys'], sample, seed=100)
+        rates = []
+        for i in range(W + K):
+            rate, dt, _, k, e = cpu_reference_leg(save_name, batch, sample, cores)
+            if i >= W:
+                rates.append((rate, dt))
+        total_t = sum(dt for _, dt in rates)
+        value = K * sample / total_t
+        line = {'metric': metric, 'value': value, 'unit': 'solves/s', 'impl': 'reference', 'n_gpus': args.gpus,
+                'steps': K, 'warmup': W, 'ms_per_step': 1e3 * total_t / K, 'higher_is_better': True,
+                'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': config,
+                'cpu_baseline': {'value': value, 'unit': 'solves/s', 'cores': cores, 'kind': 'reference',
+                                 'sample': f'{sample} instances of the workload per step, gcc -O3 instantiated reference '
+                                           f'template, {cores} pthreads over contiguous slices'},
+                'e2e': {'value': value, 'unit': 'solves/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+                'mean_k': float(k.mean()), 'n_not_converged': int((e == -1).sum())}
+        print(json.dumps(line))
+        return
+
+    # ---------------------------------------------------------------- native arm (B200)
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device -- the solver has no CPU fallback')
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    dev = torch.device('cuda', local_rank)
+    sol, spec, cfg = prebuilt.get(save_name)
+    n, m = sol.n, sol.m
+
+    # three distinct batches (3 x 112 MB of inputs > 126 MB L2), device resident and pinned-host copies
+    NB = 3
+    host, devb = [], []
+    for i in range(NB):
+        b = sysmodel.synthetic_batch(cfg['sys'], B, seed=100 + 3 * rank + i)
+        hb = {k: torch.from_numpy(v).pin_memory() for k, v in b.items()}
+        host.append(hb)
+        devb.append({k: v.to(dev) for k, v in hb.items()})
+    d_u = torch.empty((B, m), dtype=torch.float64, device=dev)
+    d_k = torch.empty(B, dtype=torch.int32, device=dev)
+    d_e = torch.empty(B, dtype=torch.int32, device=dev)
+    h_u = torch.empty((B, m), dtype=torch.float64).pin_memory()
+    h_k = torch.empty(B, dtype=torch.int32).pin_memory()
+    h_e = torch.empty(B, dtype=torch.int32).pin_memory()
+    stream = torch.cuda.current_stream(dev)
+
+    def step_dev(i):
+        b = devb[i % NB]
+        return sol.solve_batch_device(B, b['x0'].data_ptr(), b['xr'].data_ptr(), b['ur'].data_ptr(),
+                                      d_u.data_ptr(), d_k.data_ptr(), d_e.data_ptr(),
+                                      device=local_rank, stream=stream.cuda_stream)
+
+    def step_host(i):
+        b = host[i % NB]
+        return sol.solve_batch(b['x0'].numpy(), b['xr'].numpy(), b['ur'].numpy(), device=local_rank,
+                               out=(h_u.numpy(), h_k.numpy(), h_e.numpy()))[3]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- device-resident throughput
+    for i in range(W):
+        step_dev(i)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    infos = []
+    ev0.record(stream)
+    for i in range(K):
+        infos.append(step_dev(W + i))
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    t_dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    kernel_ms = float(np.mean([x['kernel_ms'] for x in infos]))
+    sum_k = float(np.mean([x['sum_k'] for x in infos]))
+    n_nc = float(np.mean([x['n_not_converged'] for x in infos]))
+    value = world * B * K / (t_dev_ms * 1e-3)
+
+    # ---- end to end through the host-buffer C-ABI call
+    for i in range(2):
+        step_host(i)
+    barrier()
+    t0 = time.perf_counter()
+    hinfos = [step_host(W + i) for i in range(K)]
+    barrier()
+    t_e2e = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = world * B * K / t_e2e
+
+    # ---- parity gate on a subset (every benchmark run) + CPU baseline, rank 0 at N = 1 only
+    cpu_baseline, parity = None, None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sample = min(B, 1 << 16)
+        b0 = {k: v.numpy() for k, v in host[(W + K - 1) % NB].items()}
+        rate1, dt1, ur_, kr, er = cpu_reference_leg(save_name, b0, sample, 1)
+        cores = os.cpu_count() or 1
+        rate_all, dt_all, _, _, _ = cpu_reference_leg(save_name, b0, sample, cores)
+        u, k, e = h_u.numpy()[:sample], h_k.numpy()[:sample], h_e.numpy()[:sample]
+        same = k == kr
+        rel = np.abs(u - ur_) / np.maximum(1.0, np.abs(ur_))
+        parity = {'compared': int(sample), 'e_flag_mismatch': int((e != er).sum()),
+                  'max_abs_dk': int(np.abs(k - kr).max()), 'n_dk_nonzero': int((~same).sum()),
+                  'u_opt_max_rel_err_same_k': float(rel[same].max()), 'tolerance': 1e-9}
+        cpu_baseline = {'value': rate1, 'unit': 'solves/s', 'cores': 1, 'kind': 'reference',
+                        'sample': f'first {sample} instances of the last timed batch; instantiated reference template, '
+                                  f'gcc -O3, DEBUG/MEASURE_TIME off; {dt1:.1f} s',
+                        'all_cores': {'value': rate_all, 'cores': cores, 'seconds': dt_all},
+                        'mean_k': float(kr.mean())}
+
+    sum_k_all = sum_over_ranks(sum_k)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    micro = run_microbench()
+    peaks, peak_kind = measured_peaks()
+    fma = fma_per_instance(spec.options.solver_key(), dims, sum_k, B)
+    achieved_tflops = 2.0 * fma / (kernel_ms * 1e-3) / 1e12
+    fp64_peak = 2.0 * micro['fp64_tfma_per_s'] if micro and 'fp64_tfma_per_s' in micro else None
+    io_bytes = B * (8 * (2 * n + m) + 8 * m + 8)
+    roofline = {'bound': 'fp64_fma', 'achieved': achieved_tflops, 'peak': fp64_peak, 'unit': 'TFLOP/s',
+                'frac': (achieved_tflops / fp64_peak) if fp64_peak else None, 'traffic': None,
+                'peak_source': 'measured in this run by spcies_b200/csrc/microbench.cu (register-only DFMA, full chip); '
+                               'MEASURED_PEAKS.json has no FP64 figure',
+                'kernel': 'spcies::fista::fista_kernel', 'kernel_ms': kernel_ms,
+                'algorithmic_fma_per_launch': fma, 'sum_k_per_launch': sum_k,
+                'hbm': {'bound': 'hbm', 'achieved': io_bytes / (kernel_ms * 1e-3) / 1e9, 'peak': peaks['hbm_gbs'],
+                        'unit': 'GB/s', 'frac': io_bytes / (kernel_ms * 1e-3) / 1e9 / peaks['hbm_gbs'],
+                        'peak_source': peak_kind + ' (MEASURED_PEAKS.json)', 'algorithmic_bytes_per_launch': io_bytes}}
+    line = {'metric': metric, 'value': value, 'unit': 'solves/s', 'n_gpus': world, 'steps': K, 'warmup': W,
+            'ms_per_step': t_dev_ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f64', 'data': 'synthetic', 'config': config,
+            'e2e': {'value': e2e_value, 'unit': 'solves/s', 'h2d_bytes_per_step': int(hinfos[-1]['h2d_bytes']),
+                    'd2h_bytes_per_step': int(hinfos[-1]['d2h_bytes']), 'ms_per_step': 1e3 * t_e2e / K,
+                    'kernel_ms': float(np.mean([x['kernel_ms'] for x in hinfos])),
+                    'h2d_ms': float(np.mean([x['h2d_ms'] for x in hinfos])),
+                    'd2h_ms': float(np.mean([x['d2h_ms'] for x in hinfos]))},
+            'gpu_launches': int(sum(x['launches'] for x in infos)) * world,
+            'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu_baseline, 'parity': parity,
+            'mean_k': sum_k_all / (world * B), 'n_not_converged_per_batch': n_nc,
+            'kernel': {'block_threads': infos[-1]['block_threads'], 'grid_blocks': infos[-1]['grid_blocks'],
+                       'smem_bytes': infos[-1]['smem_bytes'], 'regs_per_thread': infos[-1]['regs_per_thread']},
+            'microbench': micro}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,131 @@
+/*
+ * spcies_cuda.h -- C ABI of the B200 (sm_100a) batched solver backend for Spcies.
+ *
+ * Every solver generated with platform 'CUDA' is one shared library `<save_name>.so`.  It exports
+ *
+ *   (1) the reference's single-instance symbol, UNCHANGED (same name, same argument list), so a caller
+ *       written for the generated plain-C solver (examples/cl_in_C/main_cl_in_C.c:103, or the MEX gateways
+ *       formulations/+<F>/struct_<F>_<method>_C_Matlab.c) links against it as is.  It runs a batch of one;
+ *   (2) a batched entry point `<func>_batch` (new): B independent instances that share the generated system
+ *       model and differ in x0 / xr / ur (/ r_ellip / bounds);
+ *   (3) the common `spcies_cuda_*` query / housekeeping symbols below.
+ *
+ * Reference interfaces replaced (file:line in the reference tree):
+ *   laxMPC_FISTA        formulations/+laxMPC/header_laxMPC_FISTA_C.h:26      (code_laxMPC_FISTA_C.c:21)
+ *   laxMPC_ADMM         formulations/+laxMPC/header_laxMPC_ADMM_C.h:27       (code_laxMPC_ADMM_C.c:21)
+ *   equMPC_FISTA        formulations/+equMPC/header_equMPC_FISTA_C.h:25      (code_equMPC_FISTA_C.c:21)
+ *   equMPC_ADMM         formulations/+equMPC/header_equMPC_ADMM_C.h:26       (code_equMPC_ADMM_C.c:21)
+ *   ellipMPC_ADMM       formulations/+ellipMPC/header_ellipMPC_ADMM_C.h      (code_ellipMPC_ADMM_C.c)
+ *   ellipMPC_ADMM_soc   formulations/+ellipMPC/header_ellipMPC_ADMM_soc_C.h  (code_ellipMPC_ADMM_soc_C.c:20)
+ *   MPCT_EADMM          formulations/+MPCT/header_MPCT_EADMM_C.h             (code_MPCT_EADMM_C.c:18)
+ *   HMPC_ADMM           formulations/+HMPC/header_HMPC_ADMM_split_C.h:27     (code_HMPC_ADMM_split_C.c:19)
+ *
+ * Conventions
+ *   - all host arrays are row-major, instance-major: x0[B][nn_], xr[B][nn_], ur[B][mm_], r_ellip[B],
+ *     u_opt[B][mm_], k[B], e_flag[B].  One column of a MATLAB nn_ x B matrix is one instance, so an mxArray
+ *     can be passed without transposition.
+ *   - e_flag per instance keeps the reference meaning: 1 converged, -1 k_max reached
+ *     (code_laxMPC_FISTA_C.c:354-361).
+ *   - the return value (new -- the reference functions are void) is 0 on success or a cudaError_t /
+ *     SPCIES_CUDA_E* code for infrastructure errors.  There is no CPU fallback: without a usable CUDA device
+ *     every entry point fails with a non-zero code (the single-instance symbol sets *e_flag = SPCIES_CUDA_EFLAG_DEVICE).
+ *   - the caller owns every host buffer; the library owns its device buffers (created lazily per device,
+ *     released by spcies_cuda_free()).
+ *   - calls are blocking; one host thread at a time per library.
+ *
+ * The per-solver header `<save_name>.h` emitted next to `<save_name>.cu` carries the reference's #defines
+ * (nn_, mm_, NN_, k_max, tol, ...), the `sol_<save_name>` struct and the prototypes; this file holds what is
+ * common to all of them.
+ */
+#ifndef SPCIES_CUDA_H
+#define SPCIES_CUDA_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPCIES_CUDA_ABI_VERSION 1
+
+/* infrastructure error codes (positive values below 1000 are cudaError_t) */
+#define SPCIES_CUDA_EINVAL      1001   /* bad argument (NULL buffer, B < 0, ...) */
+#define SPCIES_CUDA_ENODEVICE   1002   /* no CUDA device / requested device absent */
+#define SPCIES_CUDA_EUNSUPPORTED 1003  /* option not available in this generated solver */
+#define SPCIES_CUDA_EFLAG_DEVICE (-100) /* e_flag value written by the single-instance symbol on device failure */
+
+/* arithmetic modes */
+#define SPCIES_CUDA_ARITH_FAST  0  /* fused multiply-add, reciprocal hoisting: u_opt within 1e-9 (double) of the reference */
+#define SPCIES_CUDA_ARITH_EXACT 1  /* same operations, same order, no contraction: bit-identical to gcc -O3 (no -mfma) */
+
+/* Options of a batched call.  Zero-initialise, then set what you need; NULL means all defaults. */
+typedef struct {
+    int device;              /* first CUDA device ordinal to use (default 0) */
+    int n_devices;           /* shard the batch contiguously over devices device .. device+n_devices-1 (0 or 1: one device) */
+    int arith;               /* SPCIES_CUDA_ARITH_FAST (default) | SPCIES_CUDA_ARITH_EXACT */
+    int device_pointers;     /* 1: every array argument is a DEVICE pointer on `device` (no copies; n_devices must be <= 1) */
+    const double *LB;        /* optional per-instance bounds [B][nm_] = [LBx; LBu] (the TIME_VARYING LB_in layout,  */
+    const double *UB;        /*   code_laxMPC_FISTA_C.c:102-105); NULL: the generated constants                      */
+    void *stream;            /* cudaStream_t to run on when device_pointers = 1 (NULL: the library's own stream) */
+    int block_threads;       /* 0: default chosen at generation time */
+    int grid_blocks;         /* 0: one CTA per SM */
+    int reserved[8];
+} spcies_batch_opts;
+
+/* Measurements of the last batched call (all device times from CUDA events on the launching stream). */
+typedef struct {
+    double kernel_ms;        /* solver kernel only (max over devices)                */
+    double h2d_ms, d2h_ms;   /* host<->device copies (0 with device_pointers)        */
+    double total_ms;         /* wall clock of the whole call                         */
+    long   launches;         /* number of solver-kernel launches                     */
+    long   h2d_bytes, d2h_bytes;
+    long   sum_k;            /* sum of iteration counts over the batch               */
+    long   n_not_converged;  /* instances with e_flag = -1                           */
+    int    block_threads, grid_blocks, smem_bytes, regs_per_thread;
+    int    n_devices;
+    int    reserved[7];
+} spcies_batch_info;
+
+/* ---- common symbols exported by every generated library ------------------------------------------- */
+int         spcies_cuda_abi_version(void);
+const char *spcies_cuda_solver_name(void);     /* "<F>_<method>[_<sub>]", e.g. "laxMPC_FISTA"            */
+const char *spcies_cuda_save_name(void);       /* the save_name the solver was generated with             */
+const char *spcies_cuda_precision(void);       /* "double" | "float": arithmetic type of the kernels      */
+int         spcies_cuda_dims(int *nn, int *mm, int *NN);
+long        spcies_cuda_sol_doubles(void);     /* sizeof(sol_<save_name>) / sizeof(double)                */
+int         spcies_cuda_device_count(void);    /* 0 if there is no usable device                          */
+int         spcies_cuda_kernel_attributes(int arith, int *regs, int *smem_static, int *smem_dynamic,
+                                          int *block_threads, int *local_bytes);
+void        spcies_cuda_free(void);            /* release device buffers, streams and events              */
+const char *spcies_cuda_last_error(void);
+
+/* ---- per-solver entry points ----------------------------------------------------------------------
+ * Written as macros because the `sol_<save_name>` type is generated; `<save_name>.h` expands them.
+ * NAME is the reference function name, SOL the generated `sol_<save_name>` type.                      */
+#define SPCIES_CUDA_DECLARE_SOLVER(NAME, SOL)                                                              \
+    void NAME(double *x0_in, double *xr_in, double *ur_in, double *u_opt, int *k_in, int *e_flag, SOL *sol); \
+    int NAME##_batch(long B, const double *x0, const double *xr, const double *ur,                         \
+                     double *u_opt, int *k, int *e_flag, SOL *sol /* [B] or NULL */,                       \
+                     const spcies_batch_opts *opts /* or NULL */, spcies_batch_info *info /* or NULL */)
+
+/* ellipMPC_ADMM_soc takes the size of the terminal ellipsoid at run time (code_ellipMPC_ADMM_soc_C.c:20) */
+#define SPCIES_CUDA_DECLARE_SOLVER_R(NAME, SOL)                                                            \
+    void NAME(double *x0_in, double *xr_in, double *ur_in, double *r_ellip, double *u_opt, int *k_in,      \
+              int *e_flag, SOL *sol);                                                                      \
+    int NAME##_batch(long B, const double *x0, const double *xr, const double *ur, const double *r_ellip,  \
+                     double *u_opt, int *k, int *e_flag, SOL *sol /* [B] or NULL */,                       \
+                     const spcies_batch_opts *opts /* or NULL */, spcies_batch_info *info /* or NULL */)
+
+/* The solver families and the symbols each generated library exports (checked by tests/test_abi.py):
+ *   SPCIES_CUDA_SOLVER(laxMPC_FISTA)       laxMPC_FISTA        laxMPC_FISTA_batch
+ *   SPCIES_CUDA_SOLVER(laxMPC_ADMM)        laxMPC_ADMM         laxMPC_ADMM_batch
+ *   SPCIES_CUDA_SOLVER(equMPC_FISTA)       equMPC_FISTA        equMPC_FISTA_batch
+ *   SPCIES_CUDA_SOLVER(equMPC_ADMM)        equMPC_ADMM         equMPC_ADMM_batch
+ *   SPCIES_CUDA_SOLVER(ellipMPC_ADMM)      ellipMPC_ADMM       ellipMPC_ADMM_batch
+ *   SPCIES_CUDA_SOLVER_R(ellipMPC_ADMM_soc) ellipMPC_ADMM_soc  ellipMPC_ADMM_soc_batch
+ *   SPCIES_CUDA_SOLVER(MPCT_EADMM)         MPCT_EADMM          MPCT_EADMM_batch
+ *   SPCIES_CUDA_SOLVER(HMPC_ADMM)          HMPC_ADMM           HMPC_ADMM_batch   (ADMM_split and SADMM_split)
+ */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPCIES_CUDA_H */

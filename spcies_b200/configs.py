@@ -82,3 +82,14 @@ def bench_config(name: str):
     cfg['name'] = name
     cfg['solver'] = solver
     return cfg
+
+
+def bounds_variant(sys, s: int):
+    """Deterministic variant ``s`` of the box constraints (position upper bounds ~ U[0.25, 0.35],
+    input lower bounds ~ -U[0.5, 0.8]); used to exercise per-instance bounds."""
+    rng = np.random.default_rng(1000 + s)
+    sys2 = dict(sys)
+    sys2['UBx'] = np.array(sys['UBx'], dtype=float)
+    sys2['UBx'][:sys['p']] = rng.uniform(0.25, 0.35, size=sys['p'])
+    sys2['LBu'] = -rng.uniform(0.5, 0.8, size=sys['m'])
+    return sys2

@@ -1,0 +1,160 @@
+// spcies_common.cuh -- device-side building blocks shared by every solver kernel.
+//
+//  * Arith<T, EXACT>   arithmetic policy.  EXACT = same IEEE operations in the same order as the
+//                      reference C compiled by gcc -O3 for x86-64 (no FMA contraction, true division,
+//                      correctly rounded sqrt) -> bit-identical iterates.  FAST = fused multiply-add.
+//  * clip()            the reference's saturation, `(v > LB) ? v : LB` then `(v > UB) ? UB : v`
+//                      (code_laxMPC_FISTA_C.c:488-489) -- written with the same ternaries so NaN and
+//                      LB > UB behave identically.
+//  * State<T, BLOCK>   per-instance iterates in shared memory, laid out [element][thread] so that a
+//                      warp touching element e of its 32 instances hits 32 consecutive words
+//                      (conflict-free; a 64-bit access is the minimum two wavefronts).
+//  * stage_constants() one bulk asynchronous copy (cp.async.bulk, the 1-D TMA path; SASS UBLKCP) of the
+//                      problem-constant blob global -> shared per CTA, completion on an mbarrier.
+//  * WorkQueue         persistent-kernel instance queue: one 64-bit atomic counter per launch; a lane
+//                      that finishes its instance pulls the next index (ptxas aggregates the atomics of
+//                      a warp), so the heavy-tailed iteration counts do not idle lanes.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace spcies {
+
+// ------------------------------------------------------------------------------------------------
+// Arithmetic policies
+// ------------------------------------------------------------------------------------------------
+template <typename T, bool EXACT> struct Arith;
+
+template <> struct Arith<double, false> {
+    typedef double T;
+    static __device__ __forceinline__ T add(T a, T b) { return a + b; }
+    static __device__ __forceinline__ T sub(T a, T b) { return a - b; }
+    static __device__ __forceinline__ T mul(T a, T b) { return a * b; }
+    static __device__ __forceinline__ T div(T a, T b) { return a / b; }
+    static __device__ __forceinline__ T madd(T a, T b, T c) { return fma(b, c, a); }    // a + b*c
+    static __device__ __forceinline__ T nmsub(T a, T b, T c) { return fma(-b, c, a); }  // a - b*c
+    static __device__ __forceinline__ T sqrt(T a) { return ::sqrt(a); }
+};
+template <> struct Arith<double, true> {
+    typedef double T;
+    static __device__ __forceinline__ T add(T a, T b) { return __dadd_rn(a, b); }
+    static __device__ __forceinline__ T sub(T a, T b) { return __dsub_rn(a, b); }
+    static __device__ __forceinline__ T mul(T a, T b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ T div(T a, T b) { return __ddiv_rn(a, b); }
+    static __device__ __forceinline__ T madd(T a, T b, T c) { return __dadd_rn(a, __dmul_rn(b, c)); }
+    static __device__ __forceinline__ T nmsub(T a, T b, T c) { return __dsub_rn(a, __dmul_rn(b, c)); }
+    static __device__ __forceinline__ T sqrt(T a) { return __dsqrt_rn(a); }
+};
+template <> struct Arith<float, false> {
+    typedef float T;
+    static __device__ __forceinline__ T add(T a, T b) { return a + b; }
+    static __device__ __forceinline__ T sub(T a, T b) { return a - b; }
+    static __device__ __forceinline__ T mul(T a, T b) { return a * b; }
+    static __device__ __forceinline__ T div(T a, T b) { return a / b; }
+    static __device__ __forceinline__ T madd(T a, T b, T c) { return fmaf(b, c, a); }
+    static __device__ __forceinline__ T nmsub(T a, T b, T c) { return fmaf(-b, c, a); }
+    static __device__ __forceinline__ T sqrt(T a) { return ::sqrtf(a); }
+};
+template <> struct Arith<float, true> {
+    typedef float T;
+    static __device__ __forceinline__ T add(T a, T b) { return __fadd_rn(a, b); }
+    static __device__ __forceinline__ T sub(T a, T b) { return __fsub_rn(a, b); }
+    static __device__ __forceinline__ T mul(T a, T b) { return __fmul_rn(a, b); }
+    static __device__ __forceinline__ T div(T a, T b) { return __fdiv_rn(a, b); }
+    static __device__ __forceinline__ T madd(T a, T b, T c) { return __fadd_rn(a, __fmul_rn(b, c)); }
+    static __device__ __forceinline__ T nmsub(T a, T b, T c) { return __fsub_rn(a, __fmul_rn(b, c)); }
+    static __device__ __forceinline__ T sqrt(T a) { return __fsqrt_rn(a); }
+};
+
+template <typename T> __device__ __forceinline__ T clip(T v, T lb, T ub) {
+    v = (v > lb) ? v : lb;   // maximum between v and the lower bound
+    v = (v > ub) ? ub : v;   // minimum between v and the upper bound
+    return v;
+}
+
+// |x| > tol exactly as `res = (res > 0.0) ? res : -res; if (res > tol)` (code_laxMPC_FISTA_C.c:343-344)
+template <typename T> __device__ __forceinline__ bool exceeds(T x, T tol_) {
+    T a = (x > T(0)) ? x : -x;
+    return a > tol_;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Per-instance state in shared memory: element-major, thread-minor
+// ------------------------------------------------------------------------------------------------
+template <typename T, int BLOCK> struct State {
+    T *base;   // already offset by threadIdx.x
+    __device__ __forceinline__ explicit State(T *smem_state) : base(smem_state + threadIdx.x) {}
+    __device__ __forceinline__ T ld(int e) const { return base[e * BLOCK]; }
+    __device__ __forceinline__ void st(int e, T v) const { base[e * BLOCK] = v; }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Constant blob: global -> shared, one bulk async copy per CTA
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// bytes must be a multiple of 16; dst/src 16-byte aligned.  All threads of the CTA must call it.
+__device__ __forceinline__ void stage_constants(void *smem_dst, const void *gmem_src, uint32_t bytes,
+                                                uint64_t *mbar /* in shared memory */) {
+    const uint32_t bar = smem_u32(mbar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                smem_u32(smem_dst)),
+            "l"(gmem_src), "r"(bytes), "r"(bar)
+            : "memory");
+    }
+    // every thread waits for phase 0 of the barrier (try_wait suspends in hardware, it is not a spin)
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar)
+        : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Device-side view of one batched call
+// ------------------------------------------------------------------------------------------------
+struct BatchIO {
+    long long B;
+    const double *x0, *xr, *ur, *r;   // [B][nn_], [B][nn_], [B][mm_], [B] (r: solvers with r_ellip only)
+    const double *LB, *UB;            // optional per-instance bounds [B][nm_], or nullptr
+    double *u;                        // [B][mm_]
+    int *k, *e;                       // [B]
+    double *sol;                      // optional [B][sol_doubles] (sol_<name> structs), or nullptr
+    unsigned long long *queue;        // [0] next instance index, [1] sum of k, [2] number of e_flag = -1
+};
+
+struct WorkQueue {
+    unsigned long long *q;
+    long long B;
+    __device__ __forceinline__ long long next() const {
+        unsigned long long i = atomicAdd(q, 1ULL);
+        return (i < (unsigned long long)B) ? (long long)i : -1LL;
+    }
+};
+
+// lane-local statistics -> two atomics per warp at kernel exit
+__device__ __forceinline__ void flush_stats(unsigned long long *q, unsigned long long sum_k, unsigned int n_nc) {
+    for (int o = 16; o > 0; o >>= 1) {
+        sum_k += __shfl_down_sync(0xffffffffu, sum_k, o);
+        n_nc += __shfl_down_sync(0xffffffffu, n_nc, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (sum_k) atomicAdd(q + 1, sum_k);
+        if (n_nc) atomicAdd(q + 2, (unsigned long long)n_nc);
+    }
+}
+
+}  // namespace spcies

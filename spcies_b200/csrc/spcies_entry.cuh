@@ -1,0 +1,106 @@
+// spcies_entry.cuh -- the extern "C" surface of a generated solver library (include/spcies_cuda.h).
+// Included at the end of a kernel header, after SPCIES_TRAITS is defined.  The emitted .cu defines
+//   SPCIES_FUNC          reference function name (token), e.g. laxMPC_FISTA
+//   SPCIES_SOL_T         generated sol_<save_name> type
+//   SPCIES_SOLVER_STR    "<F>_<method>[_<sub>]"
+//   SPCIES_SAVE_NAME_STR "<save_name>"
+//   SPCIES_PRECISION_STR "double" | "float"
+//   SPCIES_HAS_R         0 | 1
+#pragma once
+
+#define SPCIES_CAT_(a, b) a##b
+#define SPCIES_CAT(a, b) SPCIES_CAT_(a, b)
+
+namespace spcies {
+typedef Runtime<SPCIES_TRAITS> RT;
+
+// The reference's single-instance call = a batch of one.  Timing fields keep the reference's meaning and unit
+// (milliseconds, docs/timing.md:9-22): update_time = host->device, solve_time = kernel, polish_time = device->host.
+static inline void single_instance(double *x0_in, double *xr_in, double *ur_in, double *r_ellip, double *u_opt,
+                                   int *k_in, int *e_flag, SPCIES_SOL_T *sol) {
+    spcies_batch_info info;
+#ifdef DEBUG
+    SPCIES_SOL_T tmp;
+#endif
+    int rc = RT::get().run(1, x0_in, xr_in, ur_in, r_ellip, u_opt, k_in, e_flag,
+#ifdef DEBUG
+                           sol ? reinterpret_cast<double *>(&tmp) : nullptr,
+#else
+                           nullptr,
+#endif
+                           nullptr, &info);
+    if (rc != 0) {
+        if (e_flag) *e_flag = SPCIES_CUDA_EFLAG_DEVICE;
+        if (k_in) *k_in = 0;
+        fprintf(stderr, "spcies_cuda: %s\n", g_last_error);
+        return;
+    }
+    if (sol) {
+#ifdef DEBUG
+        *sol = tmp;
+#endif
+#if MEASURE_TIME == 1
+        sol->update_time = info.h2d_ms;
+        sol->solve_time = info.kernel_ms;
+        sol->polish_time = info.d2h_ms;
+        sol->run_time = info.total_ms;
+#endif
+    }
+}
+}  // namespace spcies
+
+extern "C" {
+
+int spcies_cuda_abi_version(void) { return SPCIES_CUDA_ABI_VERSION; }
+const char *spcies_cuda_solver_name(void) { return SPCIES_SOLVER_STR; }
+const char *spcies_cuda_save_name(void) { return SPCIES_SAVE_NAME_STR; }
+const char *spcies_cuda_precision(void) { return SPCIES_PRECISION_STR; }
+int spcies_cuda_dims(int *nn, int *mm, int *NN) {
+    if (nn) *nn = nn_;
+    if (mm) *mm = mm_;
+    if (NN) *NN = NN_;
+    return 0;
+}
+long spcies_cuda_sol_doubles(void) { return (long)(sizeof(SPCIES_SOL_T) / sizeof(double)); }
+int spcies_cuda_device_count(void) { return ::spcies::RT::get().device_count(); }
+void spcies_cuda_free(void) { ::spcies::RT::get().free_all(); }
+const char *spcies_cuda_last_error(void) { return ::spcies::g_last_error_global; }
+
+int spcies_cuda_kernel_attributes(int arith, int *regs, int *smem_static, int *smem_dynamic, int *block_threads,
+                                  int *local_bytes) {
+    if (::spcies::RT::get().device_count() <= 0)
+        return ::spcies::fail(SPCIES_CUDA_ENODEVICE, "no usable CUDA device (this library has no CPU fallback)");
+    cudaFuncAttributes fa;
+    cudaError_t e = SPCIES_TRAITS::attributes(arith, false, &fa);
+    if (e != cudaSuccess) return ::spcies::fail((int)e, "cudaFuncGetAttributes");
+    const int blk = SPCIES_TRAITS::default_block(false);
+    if (regs) *regs = fa.numRegs;
+    if (smem_static) *smem_static = (int)fa.sharedSizeBytes;
+    if (smem_dynamic) *smem_dynamic = (int)SPCIES_TRAITS::smem_bytes(blk, false);
+    if (block_threads) *block_threads = blk;
+    if (local_bytes) *local_bytes = (int)fa.localSizeBytes;
+    return 0;
+}
+
+#if SPCIES_HAS_R
+void SPCIES_FUNC(double *x0_in, double *xr_in, double *ur_in, double *r_ellip, double *u_opt, int *k_in, int *e_flag,
+                 SPCIES_SOL_T *sol) {
+    ::spcies::single_instance(x0_in, xr_in, ur_in, r_ellip, u_opt, k_in, e_flag, sol);
+}
+int SPCIES_CAT(SPCIES_FUNC, _batch)(long B, const double *x0, const double *xr, const double *ur, const double *r_ellip,
+                                    double *u_opt, int *k, int *e_flag, SPCIES_SOL_T *sol,
+                                    const spcies_batch_opts *opts, spcies_batch_info *info) {
+    return ::spcies::RT::get().run(B, x0, xr, ur, r_ellip, u_opt, k, e_flag, reinterpret_cast<double *>(sol), opts, info);
+}
+#else
+void SPCIES_FUNC(double *x0_in, double *xr_in, double *ur_in, double *u_opt, int *k_in, int *e_flag, SPCIES_SOL_T *sol) {
+    ::spcies::single_instance(x0_in, xr_in, ur_in, nullptr, u_opt, k_in, e_flag, sol);
+}
+int SPCIES_CAT(SPCIES_FUNC, _batch)(long B, const double *x0, const double *xr, const double *ur, double *u_opt, int *k,
+                                    int *e_flag, SPCIES_SOL_T *sol, const spcies_batch_opts *opts,
+                                    spcies_batch_info *info) {
+    return ::spcies::RT::get().run(B, x0, xr, ur, nullptr, u_opt, k, e_flag, reinterpret_cast<double *>(sol), opts, info);
+}
+#endif
+
+}  // extern "C"

@@ -1,0 +1,314 @@
+// spcies_host.cuh -- host side of a generated solver library: device contexts, buffers, the batched
+// call (H2D -> persistent kernel -> D2H), contiguous sharding over several GPUs (one host thread per
+// device, no collective: instances are independent), and the reference's
+// single-instance symbol implemented as a batch of one.
+//
+// A solver kernel header provides a `Traits` type:
+//   static constexpr int NN, MM, NMM;            // nn_, mm_, nm_
+//   static constexpr bool HAS_R;                 // extra r_ellip input
+//   static constexpr int SOL_DOUBLES;            // sizeof(sol_<name>)/8
+//   static constexpr bool HAS_VARB;              // per-instance bounds supported by the kernel
+//   typedef ... Consts;  static const Consts &host_consts();
+//   static int default_block();  static size_t smem_bytes(int block, bool varb);
+//   static cudaError_t launch(int arith, bool varb, int grid, int block, size_t smem, cudaStream_t s,
+//                             const BatchIO &io, const void *d_consts);
+//   static cudaError_t attributes(int arith, cudaFuncAttributes *a);
+#pragma once
+#include <cuda_runtime.h>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "spcies_common.cuh"
+#include "spcies_cuda.h"
+
+namespace spcies {
+
+static thread_local char g_last_error[512] = "";
+static char g_last_error_global[512] = "";
+
+static inline int fail(int code, const char *what) {
+    snprintf(g_last_error, sizeof g_last_error, "%s (code %d%s%s)", what, code,
+             (code > 0 && code < 1000) ? ": " : "", (code > 0 && code < 1000) ? cudaGetErrorString((cudaError_t)code) : "");
+    memcpy(g_last_error_global, g_last_error, sizeof g_last_error);
+    return code;
+}
+#define SPCIES_CK(call)                                           \
+    do {                                                          \
+        cudaError_t _e = (call);                                  \
+        if (_e != cudaSuccess) return ::spcies::fail((int)_e, #call); \
+    } while (0)
+
+struct DeviceCtx {
+    int dev = -1;
+    bool ready = false;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    void *d_consts = nullptr;
+    unsigned long long *d_queue = nullptr;
+    // device staging buffers (grown on demand)
+    long long cap = 0, cap_sol = 0, cap_b = 0;
+    double *d_x0 = nullptr, *d_xr = nullptr, *d_ur = nullptr, *d_r = nullptr, *d_LB = nullptr, *d_UB = nullptr;
+    double *d_u = nullptr, *d_sol = nullptr;
+    int *d_k = nullptr, *d_e = nullptr;
+};
+
+template <class Traits> struct Runtime {
+    std::vector<DeviceCtx> ctx;
+    std::mutex mu;
+
+    static Runtime &get() {
+        static Runtime r;
+        return r;
+    }
+
+    int device_count() {
+        int n = 0;
+        if (cudaGetDeviceCount(&n) != cudaSuccess) {
+            cudaGetLastError();
+            return 0;
+        }
+        return n;
+    }
+
+    int init_device(int dev, DeviceCtx **out) {
+        int n = device_count();
+        if (n <= 0) return fail(SPCIES_CUDA_ENODEVICE, "no usable CUDA device (this library has no CPU fallback)");
+        if (dev < 0 || dev >= n) return fail(SPCIES_CUDA_ENODEVICE, "requested CUDA device does not exist");
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            if ((int)ctx.size() < n) ctx.resize(n);
+        }
+        DeviceCtx &c = ctx[dev];
+        SPCIES_CK(cudaSetDevice(dev));
+        if (!c.ready) {
+            c.dev = dev;
+            SPCIES_CK(cudaDeviceGetAttribute(&c.sm_count, cudaDevAttrMultiProcessorCount, dev));
+            SPCIES_CK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+            for (auto &e : c.ev) SPCIES_CK(cudaEventCreate(&e));
+            const typename Traits::Consts &hc = Traits::host_consts();
+            SPCIES_CK(cudaMalloc(&c.d_consts, sizeof hc));
+            SPCIES_CK(cudaMemcpy(c.d_consts, &hc, sizeof hc, cudaMemcpyHostToDevice));
+            SPCIES_CK(cudaMalloc(&c.d_queue, 4 * sizeof(unsigned long long)));
+            c.ready = true;
+        }
+        *out = &c;
+        return 0;
+    }
+
+    template <typename P> static int grow(P **p, long long count) {
+        if (*p) SPCIES_CK(cudaFree(*p));
+        *p = nullptr;
+        SPCIES_CK(cudaMalloc((void **)p, (size_t)count * sizeof(P)));
+        return 0;
+    }
+
+    int reserve(DeviceCtx &c, long long B, bool varb, bool sol) {
+        if (B > c.cap) {
+            long long n = B + B / 8 + 64;
+            int rc;
+            if ((rc = grow(&c.d_x0, n * Traits::NN))) return rc;
+            if ((rc = grow(&c.d_xr, n * Traits::NN))) return rc;
+            if ((rc = grow(&c.d_ur, n * Traits::MM))) return rc;
+            if (Traits::HAS_R && (rc = grow(&c.d_r, n))) return rc;
+            if ((rc = grow(&c.d_u, n * Traits::MM))) return rc;
+            if ((rc = grow(&c.d_k, n))) return rc;
+            if ((rc = grow(&c.d_e, n))) return rc;
+            c.cap = n;
+        }
+        if (varb && B > c.cap_b) {
+            int rc;
+            if ((rc = grow(&c.d_LB, B * Traits::NMM))) return rc;
+            if ((rc = grow(&c.d_UB, B * Traits::NMM))) return rc;
+            c.cap_b = B;
+        }
+        if (sol && B > c.cap_sol) {
+            int rc;
+            if ((rc = grow(&c.d_sol, B * (long long)Traits::SOL_DOUBLES))) return rc;
+            c.cap_sol = B;
+        }
+        return 0;
+    }
+
+    void free_all() {
+        for (auto &c : ctx) {
+            if (!c.ready) continue;
+            cudaSetDevice(c.dev);
+            cudaFree(c.d_consts); cudaFree(c.d_queue);
+            cudaFree(c.d_x0); cudaFree(c.d_xr); cudaFree(c.d_ur); cudaFree(c.d_r); cudaFree(c.d_LB); cudaFree(c.d_UB);
+            cudaFree(c.d_u); cudaFree(c.d_sol); cudaFree(c.d_k); cudaFree(c.d_e);
+            for (auto &e : c.ev) cudaEventDestroy(e);
+            cudaStreamDestroy(c.stream);
+            c = DeviceCtx();
+        }
+    }
+
+    struct Call {
+        long long B;
+        const double *x0, *xr, *ur, *r, *LB, *UB;
+        double *u;
+        int *k, *e;
+        double *sol;
+        int arith, block, grid;
+        bool device_pointers;
+        cudaStream_t user_stream;
+    };
+    struct Result {
+        int rc = 0;
+        double kernel_ms = 0, h2d_ms = 0, d2h_ms = 0;
+        long long sum_k = 0, n_nc = 0;
+        int block = 0, grid = 0, smem = 0;
+    };
+
+    // one device, one contiguous slice [off, off+B) of the caller's arrays
+    int run_on_device(int dev, const Call &cl, Result &res) {
+        DeviceCtx *pc;
+        int rc = init_device(dev, &pc);
+        if (rc) return rc;
+        DeviceCtx &c = *pc;
+        const long long B = cl.B;
+        const bool varb = cl.LB != nullptr && cl.UB != nullptr;
+        if (varb && !Traits::HAS_VARB) return fail(SPCIES_CUDA_EUNSUPPORTED, "this solver was generated without per-instance bounds");
+        cudaStream_t s = (cl.device_pointers && cl.user_stream) ? cl.user_stream : c.stream;
+        BatchIO io;
+        memset(&io, 0, sizeof io);
+        io.B = B;
+        io.queue = c.d_queue;
+        if (cl.device_pointers) {
+            io.x0 = cl.x0; io.xr = cl.xr; io.ur = cl.ur; io.r = cl.r; io.LB = cl.LB; io.UB = cl.UB;
+            io.u = cl.u; io.k = cl.k; io.e = cl.e; io.sol = cl.sol;
+        } else {
+            if ((rc = reserve(c, B, varb, cl.sol != nullptr))) return rc;
+            SPCIES_CK(cudaEventRecord(c.ev[0], s));
+            SPCIES_CK(cudaMemcpyAsync(c.d_x0, cl.x0, (size_t)B * Traits::NN * 8, cudaMemcpyHostToDevice, s));
+            SPCIES_CK(cudaMemcpyAsync(c.d_xr, cl.xr, (size_t)B * Traits::NN * 8, cudaMemcpyHostToDevice, s));
+            SPCIES_CK(cudaMemcpyAsync(c.d_ur, cl.ur, (size_t)B * Traits::MM * 8, cudaMemcpyHostToDevice, s));
+            if (Traits::HAS_R) SPCIES_CK(cudaMemcpyAsync(c.d_r, cl.r, (size_t)B * 8, cudaMemcpyHostToDevice, s));
+            if (varb) {
+                SPCIES_CK(cudaMemcpyAsync(c.d_LB, cl.LB, (size_t)B * Traits::NMM * 8, cudaMemcpyHostToDevice, s));
+                SPCIES_CK(cudaMemcpyAsync(c.d_UB, cl.UB, (size_t)B * Traits::NMM * 8, cudaMemcpyHostToDevice, s));
+            }
+            io.x0 = c.d_x0; io.xr = c.d_xr; io.ur = c.d_ur; io.r = c.d_r;
+            io.LB = varb ? c.d_LB : nullptr; io.UB = varb ? c.d_UB : nullptr;
+            io.u = c.d_u; io.k = c.d_k; io.e = c.d_e; io.sol = cl.sol ? c.d_sol : nullptr;
+        }
+        int block = cl.block > 0 ? cl.block : Traits::default_block(varb);
+        size_t smem = Traits::smem_bytes(block, varb);
+        long long want = (B + block - 1) / block;
+        int grid = cl.grid > 0 ? cl.grid : c.sm_count;   // persistent: one CTA per SM
+        if (want < grid) grid = (int)(want > 0 ? want : 1);
+        SPCIES_CK(cudaMemsetAsync(c.d_queue, 0, 4 * sizeof(unsigned long long), s));
+        SPCIES_CK(cudaEventRecord(c.ev[1], s));
+        if (B > 0) SPCIES_CK(Traits::launch(cl.arith, varb, grid, block, smem, s, io, c.d_consts));
+        SPCIES_CK(cudaEventRecord(c.ev[2], s));
+        unsigned long long stats[4] = {0, 0, 0, 0};
+        SPCIES_CK(cudaMemcpyAsync(stats, c.d_queue, sizeof stats, cudaMemcpyDeviceToHost, s));
+        if (!cl.device_pointers) {
+            SPCIES_CK(cudaMemcpyAsync(cl.u, c.d_u, (size_t)B * Traits::MM * 8, cudaMemcpyDeviceToHost, s));
+            SPCIES_CK(cudaMemcpyAsync(cl.k, c.d_k, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+            SPCIES_CK(cudaMemcpyAsync(cl.e, c.d_e, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+            if (cl.sol)
+                SPCIES_CK(cudaMemcpyAsync(cl.sol, c.d_sol, (size_t)B * Traits::SOL_DOUBLES * 8, cudaMemcpyDeviceToHost, s));
+        }
+        SPCIES_CK(cudaEventRecord(c.ev[3], s));
+        SPCIES_CK(cudaStreamSynchronize(s));
+        SPCIES_CK(cudaGetLastError());
+        float ms = 0;
+        SPCIES_CK(cudaEventElapsedTime(&ms, c.ev[1], c.ev[2]));
+        res.kernel_ms = ms;
+        if (!cl.device_pointers) {
+            SPCIES_CK(cudaEventElapsedTime(&ms, c.ev[0], c.ev[1]));
+            res.h2d_ms = ms;
+            SPCIES_CK(cudaEventElapsedTime(&ms, c.ev[2], c.ev[3]));
+            res.d2h_ms = ms;
+        }
+        res.sum_k = (long long)stats[1];
+        res.n_nc = (long long)stats[2];
+        res.block = block; res.grid = grid; res.smem = (int)smem;
+        return 0;
+    }
+
+    int run(long long B, const double *x0, const double *xr, const double *ur, const double *r, double *u, int *k,
+            int *e, double *sol, const spcies_batch_opts *opts, spcies_batch_info *info) {
+        auto t0 = std::chrono::steady_clock::now();
+        spcies_batch_opts o;
+        memset(&o, 0, sizeof o);
+        if (opts) o = *opts;
+        if (B < 0) return fail(SPCIES_CUDA_EINVAL, "B < 0");
+        if (B > 0 && (!x0 || !xr || !ur || !u || !k || !e || (Traits::HAS_R && !r)))
+            return fail(SPCIES_CUDA_EINVAL, "NULL array argument");
+        if ((o.LB == nullptr) != (o.UB == nullptr)) return fail(SPCIES_CUDA_EINVAL, "LB and UB must be given together");
+        if (o.arith != SPCIES_CUDA_ARITH_FAST && o.arith != SPCIES_CUDA_ARITH_EXACT)
+            return fail(SPCIES_CUDA_EINVAL, "unknown arith mode");
+        int ndev = o.n_devices > 1 ? o.n_devices : 1;
+        if (o.device_pointers && ndev > 1) return fail(SPCIES_CUDA_EINVAL, "device_pointers needs n_devices <= 1");
+        int avail = device_count();
+        if (avail <= 0) return fail(SPCIES_CUDA_ENODEVICE, "no usable CUDA device (this library has no CPU fallback)");
+        if (o.device < 0 || o.device + ndev > avail) return fail(SPCIES_CUDA_ENODEVICE, "requested CUDA devices do not exist");
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            if ((int)ctx.size() < avail) ctx.resize(avail);
+        }
+        std::vector<Result> res(ndev);
+        std::vector<Call> calls(ndev);
+        const long long per = (B + ndev - 1) / ndev;
+        for (int d = 0; d < ndev; ++d) {
+            long long lo = std::min<long long>(B, d * per), hi = std::min<long long>(B, lo + per);
+            Call &c = calls[d];
+            c.B = hi - lo;
+            c.x0 = x0 + lo * Traits::NN; c.xr = xr + lo * Traits::NN; c.ur = ur + lo * Traits::MM;
+            c.r = r ? r + lo : nullptr;
+            c.LB = o.LB ? o.LB + lo * Traits::NMM : nullptr; c.UB = o.UB ? o.UB + lo * Traits::NMM : nullptr;
+            c.u = u + lo * Traits::MM; c.k = k + lo; c.e = e + lo;
+            c.sol = sol ? sol + lo * (long long)Traits::SOL_DOUBLES : nullptr;
+            c.arith = o.arith; c.block = o.block_threads; c.grid = o.grid_blocks;
+            c.device_pointers = o.device_pointers != 0;
+            c.user_stream = (cudaStream_t)o.stream;
+        }
+        if (ndev == 1) {
+            res[0].rc = run_on_device(o.device, calls[0], res[0]);
+        } else {
+            std::vector<std::thread> th;
+            std::vector<std::string> errs(ndev);
+            for (int d = 0; d < ndev; ++d)
+                th.emplace_back([&, d] {
+                    res[d].rc = run_on_device(o.device + d, calls[d], res[d]);
+                    if (res[d].rc) errs[d] = g_last_error;
+                });
+            for (auto &t : th) t.join();
+            for (int d = 0; d < ndev; ++d)
+                if (res[d].rc) snprintf(g_last_error, sizeof g_last_error, "device %d: %s", o.device + d, errs[d].c_str());
+        }
+        for (int d = 0; d < ndev; ++d)
+            if (res[d].rc) return res[d].rc;
+        if (info) {
+            memset(info, 0, sizeof *info);
+            for (int d = 0; d < ndev; ++d) {
+                info->kernel_ms = std::max(info->kernel_ms, res[d].kernel_ms);
+                info->h2d_ms = std::max(info->h2d_ms, res[d].h2d_ms);
+                info->d2h_ms = std::max(info->d2h_ms, res[d].d2h_ms);
+                info->sum_k += res[d].sum_k;
+                info->n_not_converged += res[d].n_nc;
+                info->launches += calls[d].B > 0 ? 1 : 0;
+            }
+            info->block_threads = res[0].block; info->grid_blocks = res[0].grid; info->smem_bytes = res[0].smem;
+            info->n_devices = ndev;
+            if (!o.device_pointers) {
+                const long long varb = (o.LB ? 2LL * Traits::NMM : 0);
+                info->h2d_bytes = B * 8 * (2 * Traits::NN + Traits::MM + (Traits::HAS_R ? 1 : 0) + varb);
+                info->d2h_bytes = B * (8 * Traits::MM + 8) + (sol ? B * 8LL * Traits::SOL_DOUBLES : 0);
+            }
+            cudaFuncAttributes fa;
+            if (Traits::attributes(o.arith, o.LB != nullptr, &fa) == cudaSuccess) info->regs_per_thread = fa.numRegs;
+            info->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        }
+        return 0;
+    }
+};
+
+}  // namespace spcies

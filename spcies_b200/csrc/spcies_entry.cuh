@@ -49,6 +49,10 @@ static inline void single_instance(double *x0_in, double *xr_in, double *ur_in, 
 }
 }  // namespace spcies
 
+// Every generated library is built with -fvisibility=hidden -fno-gnu-unique: only the C ABI below is exported, and
+// template statics / inline functions are NOT unified across libraries.  (Without this, two generated solvers loaded
+// into one process would share one Runtime<> singleton -- and with it the first library's device constants.)
+#pragma GCC visibility push(default)
 extern "C" {
 
 int spcies_cuda_abi_version(void) { return SPCIES_CUDA_ABI_VERSION; }
@@ -104,3 +108,4 @@ int SPCIES_CAT(SPCIES_FUNC, _batch)(long B, const double *x0, const double *xr, 
 #endif
 
 }  // extern "C"
+#pragma GCC visibility pop

@@ -27,8 +27,28 @@
 #pragma once
 #include "spcies_host.cuh"
 
+// Kernel variant (compile-time, chosen by the generator):
+//   SPCIES_MU_REGS = 0   stage loops rolled; the forward-substitution result mu[N][n] goes through shared memory and
+//                        [A B] is pinned in registers.  Smallest code, 200 doubles of shared memory per instance (N=10).
+//   SPCIES_MU_REGS = 1   stage loops fully unrolled; mu[N][n] stays in registers between the two passes and [A B] is
+//                        read from shared memory (warp-broadcast loads).  140 doubles of shared memory per instance,
+//                        i.e. 6 instead of 4 resident warps per SM at N=10, and ptxas can overlap the triangular solve of
+//                        stage l with the z / residual products of stage l+1.
+// Measured on B200 (profiles/r1_fista_variants.md): variant 1 is 1.66x SLOWER than variant 0 at N = 10 -- its 88 KB of
+// straight-line code misses the instruction cache (stall reason no_instruction = 2.2 per issue).  Default: 0.
+#ifndef SPCIES_MU_REGS
+#define SPCIES_MU_REGS 0
+#endif
 #ifndef SPCIES_UNROLL_STAGES
-#define SPCIES_UNROLL_STAGES 1
+#define SPCIES_UNROLL_STAGES (SPCIES_MU_REGS ? NN_ : 1)
+#endif
+
+// Stage boundary of the unrolled variant: keeps the compiler from hoisting the (alias-free) shared-memory loads of
+// all ten stages to the top of the pass, which would spill hundreds of registers.
+#if SPCIES_MU_REGS
+#define SPCIES_STAGE_FENCE() asm volatile("" ::: "memory")
+#else
+#define SPCIES_STAGE_FENCE() do { } while (0)
 #endif
 
 namespace spcies {
@@ -38,12 +58,14 @@ typedef SPCIES_REAL real;
 constexpr int n = nn_, m = mm_, nm = nm_, N = NN_;
 constexpr bool TERMINAL = (SPCIES_TERMINAL != 0);
 constexpr int UNROLL_STAGES = SPCIES_UNROLL_STAGES;
+constexpr bool MU_REGS = (SPCIES_MU_REGS != 0);
+static_assert(!MU_REGS || UNROLL_STAGES >= NN_, "mu in registers needs fully unrolled stage loops");
 
 // shared-memory state elements per instance
 constexpr int OFF_Y = 0;                 // y[N][n]      linearisation point
 constexpr int OFF_LAM = OFF_Y + N * n;   // lambda[N][n]
-constexpr int OFF_MU = OFF_LAM + N * n;  // mu[N][n]     W-solve workspace (forward result)
-constexpr int OFF_B = OFF_MU + N * n;    // b[n] = -A x0
+constexpr int OFF_MU = OFF_LAM + N * n;  // mu[N][n]     W-solve workspace (forward result; only if !MU_REGS)
+constexpr int OFF_B = OFF_MU + (MU_REGS ? 0 : N * n);   // b[n] = -A x0
 constexpr int OFF_Q = OFF_B + n;         // q[nm] = [Q xr; R ur]   (Q, R stored negated)
 constexpr int OFF_QT = OFF_Q + nm;       // qT[n] = T xr (lax)  |  xr (equ)
 constexpr int STATE_FIXED = OFF_QT + n;
@@ -121,9 +143,11 @@ __device__ __forceinline__ void z_stage(real (&z)[nm], const real (&AB)[n][nm], 
 #pragma unroll
     for (int j = 0; j < nm; ++j) z[j] = q[j];
 #pragma unroll
-    for (int i = 0; i < n; ++i)
+    for (int i = 0; i < n; ++i) {
+        SPCIES_STAGE_FENCE();   // one row of [A B] in flight at a time
 #pragma unroll
         for (int j = 0; j < nm; ++j) z[j] = A::nmsub(z[j], AB[i][j], yn[i]);
+    }
 #pragma unroll
     for (int j = 0; j < n; ++j) z[j] = A::add(z[j], yl[j]);
 #pragma unroll
@@ -177,12 +201,17 @@ __global__ void __launch_bounds__(BLOCK, 1) fista_kernel(const BatchIO io, const
     auto ST = [&](int e, real v) { stbase[e * BLOCK] = v; };
     Bounds<VARB> bd{C, stbase, BLOCK};
 
-    // [A B] is reused by every stage of every iteration: keep it in registers
+    // [A B] is reused by every stage of every iteration: pinned in registers (MU_REGS = 0) or read through
+    // warp-broadcast shared-memory loads (MU_REGS = 1, where the registers hold mu instead)
+#if SPCIES_MU_REGS
+    const real(&AB)[n][nm] = C->AB;
+#else
     real AB[n][nm];
 #pragma unroll
     for (int i = 0; i < n; ++i)
 #pragma unroll
         for (int j = 0; j < nm; ++j) AB[i][j] = C->AB[i][j];
+#endif
 
     const real tol_ = (real)tol;
     WorkQueue wq{io.queue, io.B};
@@ -238,6 +267,9 @@ __global__ void __launch_bounds__(BLOCK, 1) fista_kernel(const BatchIO io, const
 
         // ================= pass A: z(y) -> residual -> exit test -> forward substitution =================
         real q[nm], yl[n], yn[n], zp[nm], zc[nm], mu[n], mprev[n], u0[m];
+#if SPCIES_MU_REGS
+        real mus[N - 1][n];   // forward-substitution result of stages 0..N-2 (stage N-1 stays in `mu`)
+#endif
         bool over = false;
 #pragma unroll
         for (int j = 0; j < nm; ++j) q[j] = LD(OFF_Q + j);
@@ -266,7 +298,11 @@ __global__ void __launch_bounds__(BLOCK, 1) fista_kernel(const BatchIO io, const
         fwd_block<A>(mu, mprev, C, 0, true);
 #pragma unroll
         for (int j = 0; j < n; ++j) {
+#if SPCIES_MU_REGS
+            mus[0][j] = mu[j];
+#else
             ST(OFF_MU + j, mu[j]);
+#endif
             mprev[j] = mu[j];
             yl[j] = yn[j];
         }
@@ -276,11 +312,13 @@ __global__ void __launch_bounds__(BLOCK, 1) fista_kernel(const BatchIO io, const
         // stages 1 .. N-2                                                  :494-519, :557-564, :593-603
 #pragma unroll UNROLL_STAGES
         for (int l = 1; l < N - 1; ++l) {
+            SPCIES_STAGE_FENCE();
 #pragma unroll
             for (int j = 0; j < n; ++j) yn[j] = LD(OFF_Y + (l + 1) * n + j);
             z_stage<A, VARB>(zc, AB, yl, yn, q, C, bd, l);
 #pragma unroll
             for (int j = 0; j < n; ++j) {
+                SPCIES_STAGE_FENCE();
                 real r = zc[j];
 #pragma unroll
                 for (int i = 0; i < nm; ++i) r = A::nmsub(r, AB[j][i], zp[i]);
@@ -290,7 +328,11 @@ __global__ void __launch_bounds__(BLOCK, 1) fista_kernel(const BatchIO io, const
             fwd_block<A>(mu, mprev, C, l, false);
 #pragma unroll
             for (int j = 0; j < n; ++j) {
+#if SPCIES_MU_REGS
+                mus[l][j] = mu[j];
+#else
                 ST(OFF_MU + l * n + j, mu[j]);
+#endif
                 mprev[j] = mu[j];
                 yl[j] = yn[j];
             }
@@ -383,8 +425,13 @@ __global__ void __launch_bounds__(BLOCK, 1) fista_kernel(const BatchIO io, const
         }
 #pragma unroll UNROLL_STAGES
         for (int l = N - 2; l >= 0; --l) {
+            SPCIES_STAGE_FENCE();
 #pragma unroll
+#if SPCIES_MU_REGS
+            for (int j = 0; j < n; ++j) mu[j] = mus[l][j];
+#else
             for (int j = 0; j < n; ++j) mu[j] = LD(OFF_MU + l * n + j);
+#endif
             bwd_block<A>(mu, mnext, C, l, false);
 #pragma unroll
             for (int j = 0; j < n; ++j) {

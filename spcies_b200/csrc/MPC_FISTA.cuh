@@ -468,8 +468,9 @@ struct Traits {
         kern<<<grid, BLOCK, smem, s>>>(io, (const spcies_consts *)dc);
         return cudaGetLastError();
     }
+    static size_t scratch_bytes(int, int, bool) { return 0; }
     static cudaError_t launch(int arith, bool varb, int grid, int block, size_t smem, cudaStream_t s, const BatchIO &io,
-                              const void *dc) {
+                              const void *dc, void *) {
         const bool ex = arith == SPCIES_CUDA_ARITH_EXACT;
         if (varb) {
             if (block != BLOCK_VARB) return cudaErrorInvalidConfiguration;

@@ -10,9 +10,10 @@
 //   static constexpr bool HAS_VARB;              // per-instance bounds supported by the kernel
 //   typedef ... Consts;  static const Consts &host_consts();
 //   static int default_block();  static size_t smem_bytes(int block, bool varb);
+//   static size_t scratch_bytes(int grid, int block, bool varb);   // global per-instance state, 0 if none
 //   static cudaError_t launch(int arith, bool varb, int grid, int block, size_t smem, cudaStream_t s,
-//                             const BatchIO &io, const void *d_consts);
-//   static cudaError_t attributes(int arith, cudaFuncAttributes *a);
+//                             const BatchIO &io, const void *d_consts, void *d_scratch);
+//   static cudaError_t attributes(int arith, bool varb, cudaFuncAttributes *a);
 #pragma once
 #include <cuda_runtime.h>
 #include <chrono>
@@ -56,6 +57,8 @@ struct DeviceCtx {
     double *d_x0 = nullptr, *d_xr = nullptr, *d_ur = nullptr, *d_r = nullptr, *d_LB = nullptr, *d_UB = nullptr;
     double *d_u = nullptr, *d_sol = nullptr;
     int *d_k = nullptr, *d_e = nullptr;
+    void *d_scratch = nullptr;   // per-instance state of solvers whose iterates do not fit shared memory
+    size_t cap_scratch = 0;
 };
 
 template <class Traits> struct Runtime {
@@ -141,7 +144,7 @@ template <class Traits> struct Runtime {
             cudaSetDevice(c.dev);
             cudaFree(c.d_consts); cudaFree(c.d_queue);
             cudaFree(c.d_x0); cudaFree(c.d_xr); cudaFree(c.d_ur); cudaFree(c.d_r); cudaFree(c.d_LB); cudaFree(c.d_UB);
-            cudaFree(c.d_u); cudaFree(c.d_sol); cudaFree(c.d_k); cudaFree(c.d_e);
+            cudaFree(c.d_u); cudaFree(c.d_sol); cudaFree(c.d_k); cudaFree(c.d_e); cudaFree(c.d_scratch);
             for (auto &e : c.ev) cudaEventDestroy(e);
             cudaStreamDestroy(c.stream);
             c = DeviceCtx();
@@ -202,9 +205,16 @@ template <class Traits> struct Runtime {
         long long want = (B + block - 1) / block;
         int grid = cl.grid > 0 ? cl.grid : c.sm_count;   // persistent: one CTA per SM
         if (want < grid) grid = (int)(want > 0 ? want : 1);
+        const size_t need_scratch = Traits::scratch_bytes(grid, block, varb);
+        if (need_scratch > c.cap_scratch) {
+            if (c.d_scratch) SPCIES_CK(cudaFree(c.d_scratch));
+            c.d_scratch = nullptr;
+            SPCIES_CK(cudaMalloc(&c.d_scratch, need_scratch));
+            c.cap_scratch = need_scratch;
+        }
         SPCIES_CK(cudaMemsetAsync(c.d_queue, 0, 4 * sizeof(unsigned long long), s));
         SPCIES_CK(cudaEventRecord(c.ev[1], s));
-        if (B > 0) SPCIES_CK(Traits::launch(cl.arith, varb, grid, block, smem, s, io, c.d_consts));
+        if (B > 0) SPCIES_CK(Traits::launch(cl.arith, varb, grid, block, smem, s, io, c.d_consts, c.d_scratch));
         SPCIES_CK(cudaEventRecord(c.ev[2], s));
         unsigned long long stats[4] = {0, 0, 0, 0};
         SPCIES_CK(cudaMemcpyAsync(stats, c.d_queue, sizeof stats, cudaMemcpyDeviceToHost, s));

@@ -1,0 +1,154 @@
+"""GPU parity of the solver kernels against the instantiated reference C solver (oracle/_ref)."""
+import numpy as np
+import pytest
+
+from spcies_b200 import prebuilt, sysmodel
+from spcies_b200.solver import ARITH_EXACT, ARITH_FAST
+
+pytestmark = pytest.mark.gpu
+
+# generated solver -> (golden vector in tests/golden/reference_golden.json, sol field compared with it)
+# (None: the reference's HMPC golden vector is stale -- SURVEY.md section 4 -- so HMPC is pinned by the instantiated C only)
+GOLD = {'T_laxMPC_FISTA': ('laxMPC_FISTA', 'z'), 'T_equMPC_FISTA': ('equMPC_FISTA', 'z'),
+        'T_laxMPC_ADMM': ('laxMPC_ADMM', 'z'), 'T_equMPC_ADMM': ('equMPC_ADMM', 'z'),
+        'T_ellipMPC_ADMM': ('ellipMPC_ADMM', 'z'), 'T_ellipMPC_ADMM_soc': ('ellipMPC_ADMM_soc', 'z'),
+        'T_MPCT_EADMM': ('MPCT_EADMM', 'z1'), 'T_HMPC_ADMM_split': None, 'T_HMPC_SADMM_split': None}
+TEST_SOLVERS = list(GOLD)
+BATCH_SOLVERS = TEST_SOLVERS + ['C2_laxMPC_FISTA', 'C3_equMPC_ADMM', 'C4_ellipMPC_ADMM_soc']
+LONG_HORIZON = ['C5a_HMPC_SADMM_split', 'C5b_MPCT_EADMM']      # N = 50: per-instance state in the global scratch
+
+
+def _batch(sol, cfg, B, seed):
+    b = sysmodel.synthetic_batch(cfg['sys'], B, seed=seed, with_r=sol.has_r)
+    return b, (dict(r=b['r']) if sol.has_r else {})
+
+
+def _cmp_fields(spec, s, sr, exact):
+    """Compare every debug vector of sol_<name>.  MPCT_EADMM: the reference's DEBUG copy of lambda only fills the
+    first nn_ of every nm_ entries, packed (code_MPCT_EADMM_C.c:509-513) -- compare those."""
+    for f, _len in spec.sol_fields:
+        a, b = s[f], sr[f]
+        if spec.func_name == 'MPCT_EADMM' and f == 'lambda':
+            n, nm = spec.dims['n'], spec.dims['n'] + spec.dims['m']
+            nblk = a.shape[-1] // nm
+            a = a.reshape(a.shape[:-1] + (nblk, nm))[..., :n].reshape(a.shape[:-1] + (nblk * n,))
+            b = b[..., :nblk * n]
+        if exact:
+            assert np.array_equal(a, b), f
+        else:
+            assert np.max(np.abs(a - b)) <= 1e-9, f
+
+
+def _ref(name):
+    from oracle import refs
+    return refs.get(name)[0]
+
+
+def _rel_err(u, v):
+    return np.max(np.abs(u - v) / np.maximum(1.0, np.abs(v)))
+
+
+@pytest.mark.parametrize('name', TEST_SOLVERS)
+def test_single_instance_symbol_vs_golden_and_reference(name, golden):
+    """Reference test point (tests/spcies_tester.m:114-116) through the UNCHANGED single-instance symbol."""
+    sol, spec, cfg = prebuilt.get(name)
+    st = cfg['status']
+    r = cfg['param'].get('r', None) if sol.has_r else None
+    u, k, e, s = sol.solve(st['x'], st['xr'], st['ur'], r)
+    ur_, kr, er, sr = _ref(name).solve(st['x'], st['xr'], st['ur'], r)
+    assert e == er == 1
+    assert abs(k - kr) <= 1
+    if GOLD[name] is not None:
+        gold_name, field = GOLD[name]
+        z_opt = np.array(golden[gold_name]['z_opt'])
+        z = s[field][:len(z_opt)]                            # ADMM_soc compares z(1:end-1), test_ellipMPC_ADMM_soc.m:46
+        assert np.max(np.abs(z - z_opt)) <= 1e-4             # tol_opt of tests/spcies_tester.m:261
+    _cmp_fields(spec, s, sr, exact=False)
+    assert _rel_err(u, ur_) <= 1e-9
+
+
+@pytest.mark.parametrize('name', BATCH_SOLVERS)
+def test_exact_mode_is_bit_identical(name):
+    """ARITH_EXACT: same IEEE operations in the same order as gcc -O3 => identical bits, k and e_flag."""
+    sol, spec, cfg = prebuilt.get(name)
+    batch, kw = _batch(sol, cfg, 4096 if 'FISTA' in name else 512, seed=1)
+    u, k, e, info = sol.solve_batch(batch['x0'], batch['xr'], batch['ur'], arith=ARITH_EXACT, **kw)
+    ur_, kr, er = _ref(name).solve_batch(batch['x0'], batch['xr'], batch['ur'], threads=8, **kw)
+    assert np.array_equal(e, er)
+    assert np.array_equal(k, kr)
+    assert np.array_equal(u.view(np.uint64), ur_.view(np.uint64))
+    assert info['sum_k'] == int(k.sum())
+    assert info['n_not_converged'] == int((e == -1).sum())
+
+
+@pytest.mark.parametrize('name', BATCH_SOLVERS)
+def test_fast_mode_parity(name):
+    """ARITH_FAST (FMA): u_opt within 1e-9 relative, e_flag identical, |dk| <= 1 (BASELINE.json north_star)."""
+    sol, spec, cfg = prebuilt.get(name)
+    batch, kw = _batch(sol, cfg, 8192 if 'FISTA' in name else 512, seed=2)
+    u, k, e, info = sol.solve_batch(batch['x0'], batch['xr'], batch['ur'], arith=ARITH_FAST, **kw)
+    ur_, kr, er = _ref(name).solve_batch(batch['x0'], batch['xr'], batch['ur'], threads=8, **kw)
+    assert np.array_equal(e, er)
+    assert np.max(np.abs(k - kr)) <= 1
+    same = k == kr
+    assert _rel_err(u[same], ur_[same]) <= 1e-9
+    # an instance whose k moved by one stops one iterate earlier/later: compare at the solver tolerance
+    if (~same).any():
+        assert _rel_err(u[~same], ur_[~same]) <= 10 * float(spec.define('tol', spec.define('tol_p')))
+
+
+@pytest.mark.parametrize('name', TEST_SOLVERS)
+def test_debug_payload_batch(name):
+    """sol_<name> payload (DEBUG builds) of a ragged batch, exact mode: every vector bit-identical."""
+    sol, spec, cfg = prebuilt.get(name)
+    batch, kw = _batch(sol, cfg, 257 if 'HMPC' not in name else 65, seed=3)
+    u, k, e, info, s = sol.solve_batch(batch['x0'], batch['xr'], batch['ur'], arith=ARITH_EXACT, want_sol=True, **kw)
+    ur_, kr, er, sr = _ref(name).solve_batch(batch['x0'], batch['xr'], batch['ur'], want_sol=True, threads=8, **kw)
+    assert np.array_equal(k, kr) and np.array_equal(e, er)
+    _cmp_fields(spec, s, sr, exact=True)
+
+
+@pytest.mark.parametrize('name', LONG_HORIZON)
+def test_long_horizon_exact(name):
+    """N = 50 configurations of BASELINE.json configs[4] (state in the L2-resident global scratch), exact mode."""
+    sol, spec, cfg = prebuilt.get(name)
+    batch, kw = _batch(sol, cfg, 192 if 'HMPC' in name else 640, seed=8)
+    u, k, e, info = sol.solve_batch(batch['x0'], batch['xr'], batch['ur'], arith=ARITH_EXACT, **kw)
+    ur_, kr, er = _ref(name).solve_batch(batch['x0'], batch['xr'], batch['ur'], threads=16, **kw)
+    assert np.array_equal(e, er) and np.array_equal(k, kr)
+    assert np.array_equal(u, ur_)
+
+
+def test_per_instance_bounds_match_regenerated_reference():
+    """Per-instance bounds (opts.LB/UB): every distinct bound set must reproduce a reference solver that was
+    generated with those bounds as constants."""
+    from oracle import refs
+    sol, spec, cfg = prebuilt.get('C2_laxMPC_FISTA')
+    B = 96
+    batch = sysmodel.synthetic_batch(cfg['sys'], B, seed=4)
+    n, m = sol.n, sol.m
+    variants = [refs.get_bounds_variant('C2_laxMPC_FISTA', s) for s in range(refs.N_BOUNDS_VARIANTS)]
+    which = np.arange(B) % len(variants)
+    LB = np.stack([np.concatenate([variants[w][1]['LBx'], variants[w][1]['LBu']]) for w in which])
+    UB = np.stack([np.concatenate([variants[w][1]['UBx'], variants[w][1]['UBu']]) for w in which])
+    # the regenerated reference sees its bounds through the generator's %1.15f text (dec_var.m:259)
+    r15 = np.vectorize(lambda v: float('%1.15f' % v))
+    LB, UB = r15(LB), r15(UB)
+    u, k, e, info = sol.solve_batch(batch['x0'], batch['xr'], batch['ur'], LB=LB, UB=UB, arith=ARITH_EXACT)
+    for s, (ref, _) in enumerate(variants):
+        idx = np.nonzero(which == s)[0]
+        ur_, kr, er = ref.solve_batch(batch['x0'][idx], batch['xr'][idx], batch['ur'][idx])
+        assert np.array_equal(k[idx], kr) and np.array_equal(e[idx], er)
+        assert np.array_equal(u[idx], ur_)
+
+
+def test_empty_and_ragged_batches():
+    sol, spec, cfg = prebuilt.get('C2_laxMPC_FISTA')
+    for B in (0, 1, 31, 33, 127, 129, 1000):
+        batch = sysmodel.synthetic_batch(cfg['sys'], max(B, 1), seed=6)
+        x0, xr, ur = batch['x0'][:B], batch['xr'][:B], batch['ur'][:B]
+        u, k, e, info = sol.solve_batch(x0, xr, ur, arith=ARITH_EXACT)
+        assert u.shape == (B, sol.m)
+        if B:
+            ur_, kr, er = _ref('C2_laxMPC_FISTA').solve_batch(x0, xr, ur)
+            assert np.array_equal(u, ur_) and np.array_equal(k, kr) and np.array_equal(e, er)

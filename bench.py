@@ -232,19 +232,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    from spcies_b200.sharding import reduce_scalar
+
     def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return reduce_scalar(x, 'max', dev)
 
     def sum_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+        return reduce_scalar(x, 'sum', dev)
 
     # ---- device-resident throughput
     for i in range(W):

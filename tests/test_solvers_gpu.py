@@ -152,3 +152,16 @@ def test_empty_and_ragged_batches():
         if B:
             ur_, kr, er = _ref('C2_laxMPC_FISTA').solve_batch(x0, xr, ur)
             assert np.array_equal(u, ur_) and np.array_equal(k, kr) and np.array_equal(e, er)
+
+
+def test_plain_c_harness_runs():
+    """harness/main_batch.c: the reference's plain-C caller pattern (examples/cl_in_C/main_cl_in_C.c) on the CUDA library."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, 'harness', 'main_batch')
+    assert os.path.exists(exe), 'run __graft_entry__.build() first'
+    out = subprocess.run([exe, '4096', '2'], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    assert 'single solve: u = [0.800000 0.800000]' in out.stdout and 'e_flag = 1' in out.stdout
+    assert 'closed loop step 2' in out.stdout

@@ -60,12 +60,13 @@ class ClockSampler:
     def __init__(self, index=0):
         self.index = index
         self.proc = None
-        self.lines = []
+        self.lines = []          # (host time of arrival, csv line)
+        self.windows = []        # [t0, t1] of the timed regions
 
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                          '--format=csv,noheader,nounits', '-lms', '20'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -74,7 +75,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
     def stop(self):
         if self.proc is None:
@@ -86,7 +87,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons, pw = [], [], set(), []
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for ln in self.lines:
+        for ts, ln in self.lines:
+            if self.windows and not any(a <= ts <= b + 0.03 for a, b in self.windows):
+                continue             # keep only the samples taken while a timed region was running
             f = [x.strip() for x in ln.split(',')]
             if len(f) < 7:
                 continue
@@ -136,7 +139,7 @@ def cpu_reference_leg(save_name, batch, sample, threads):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--config', default='C2')
     ap.add_argument('--impl', default='native', choices=['native', 'reference'])
@@ -241,20 +244,21 @@ def main():
         return reduce_scalar(x, 'sum', dev)
 
     # ---- device-resident throughput
-    for i in range(W):
-        step_dev(i)
     sampler = ClockSampler(local_rank)
-    barrier()
     if rank == 0:
         sampler.start()
+    for i in range(W):
+        step_dev(i)
+    barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     infos = []
+    tw0 = time.perf_counter()
     ev0.record(stream)
     for i in range(K):
         infos.append(step_dev(W + i))
     ev1.record(stream)
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    sampler.windows.append((tw0, time.perf_counter()))
     t_dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
     kernel_ms = float(np.mean([x['kernel_ms'] for x in infos]))
     sum_k = float(np.mean([x['sum_k'] for x in infos]))
@@ -268,13 +272,15 @@ def main():
     t0 = time.perf_counter()
     hinfos = [step_host(W + i) for i in range(K)]
     barrier()
+    sampler.windows.append((t0, time.perf_counter()))
     t_e2e = max_over_ranks(time.perf_counter() - t0)
+    clocks = sampler.stop() if rank == 0 else None
     e2e_value = world * B * K / t_e2e
 
     # ---- parity gate on a subset (every benchmark run) + CPU baseline, rank 0 at N = 1 only
     cpu_baseline, parity = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sample = min(B, 1 << 16)
+        sample = min(B, 1 << 19)                       # ~13 s on one core (mean k = 32)
         b0 = {k: v.numpy() for k, v in host[(W + K - 1) % NB].items()}
         rate1, dt1, ur_, kr, er = cpu_reference_leg(save_name, b0, sample, 1)
         cores = os.cpu_count() or 1
@@ -307,7 +313,7 @@ def main():
                 'frac': (achieved_tflops / fp64_peak) if fp64_peak else None, 'traffic': None,
                 'peak_source': 'measured in this run by spcies_b200/csrc/microbench.cu (register-only DFMA, full chip); '
                                'MEASURED_PEAKS.json has no FP64 figure',
-                'kernel': 'spcies::fista::fista_kernel', 'kernel_ms': kernel_ms,
+                'kernel': 'spcies::fista::fista_kernel (per step: throughput launch + tail launch)', 'kernel_ms': kernel_ms,
                 'algorithmic_fma_per_launch': fma, 'sum_k_per_launch': sum_k,
                 'hbm': {'bound': 'hbm', 'achieved': io_bytes / (kernel_ms * 1e-3) / 1e9, 'peak': peaks['hbm_gbs'],
                         'unit': 'GB/s', 'frac': io_bytes / (kernel_ms * 1e-3) / 1e9 / peaks['hbm_gbs'],
@@ -324,7 +330,10 @@ def main():
             'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu_baseline, 'parity': parity,
             'mean_k': sum_k_all / (world * B), 'n_not_converged_per_batch': n_nc,
             'kernel': {'block_threads': infos[-1]['block_threads'], 'grid_blocks': infos[-1]['grid_blocks'],
-                       'smem_bytes': infos[-1]['smem_bytes'], 'regs_per_thread': infos[-1]['regs_per_thread']},
+                       'smem_bytes': infos[-1]['smem_bytes'], 'regs_per_thread': infos[-1]['regs_per_thread'],
+                       'launches_per_step': infos[-1]['launches'],
+                       'queue_dry_ms': infos[-1]['drain_us'] / 1e3, 'span_ms': infos[-1]['span_us'] / 1e3,
+                       'parked_instances': infos[-1]['parked']},
             'microbench': micro}
     print(json.dumps(line))
     if world > 1:

@@ -56,6 +56,13 @@ extern "C" {
 #define SPCIES_CUDA_ARITH_FAST  0  /* fused multiply-add, reciprocal hoisting: u_opt within 1e-9 (double) of the reference */
 #define SPCIES_CUDA_ARITH_EXACT 1  /* same operations, same order, no contraction: bit-identical to gcc -O3 (no -mfma) */
 
+/* Tail handling.  Iteration counts are heavy-tailed; with AUTO, solvers that support it run a large batch as two
+ * launches: the first parks the few instances that are still iterating shortly after the instance queue ran dry, the
+ * second resumes them with one warp per SM scheduler (much faster per iteration).  Results do not depend on the mode. */
+#define SPCIES_CUDA_TAIL_AUTO   0
+#define SPCIES_CUDA_TAIL_SINGLE 1  /* always one launch that runs every instance to its end */
+#define SPCIES_CUDA_TAIL_TWO_PHASE 2 /* always park & resume (AUTO does so for batches larger than four waves of lanes) */
+
 /* Options of a batched call.  Zero-initialise, then set what you need; NULL means all defaults. */
 typedef struct {
     int device;              /* first CUDA device ordinal to use (default 0) */
@@ -67,7 +74,9 @@ typedef struct {
     void *stream;            /* cudaStream_t to run on when device_pointers = 1 (NULL: the library's own stream) */
     int block_threads;       /* 0: default chosen at generation time */
     int grid_blocks;         /* 0: one CTA per SM */
-    int reserved[8];
+    int tail_mode;           /* SPCIES_CUDA_TAIL_AUTO (default) | _SINGLE | _TWO_PHASE, see above */
+    int tail_grace;          /* iterations an instance may still run after the queue ran dry before it is parked (0: 32) */
+    int reserved[6];
 } spcies_batch_opts;
 
 /* Measurements of the last batched call (all device times from CUDA events on the launching stream). */
@@ -81,7 +90,10 @@ typedef struct {
     long   n_not_converged;  /* instances with e_flag = -1                           */
     int    block_threads, grid_blocks, smem_bytes, regs_per_thread;
     int    n_devices;
-    int    reserved[7];
+    int    drain_us;         /* kernel start -> first lane finds the instance queue empty (us, device globaltimer) */
+    int    span_us;          /* kernel start -> last warp leaves (us); span_us - drain_us = tail of the slowest instances */
+    int    parked;           /* instances handed from the first to the second launch (tail handling), 0 with one launch */
+    int    reserved[4];
 } spcies_batch_info;
 
 /* ---- common symbols exported by every generated library ------------------------------------------- */

@@ -133,8 +133,25 @@ struct BatchIO {
     double *u;                        // [B][mm_]
     int *k, *e;                       // [B]
     double *sol;                      // optional [B][sol_doubles] (sol_<name> structs), or nullptr
-    unsigned long long *queue;        // [0] next instance index, [1] sum of k, [2] number of e_flag = -1
+    unsigned long long *queue;        // [0] next instance index, [1] sum of k, [2] number of e_flag = -1,
+                                      // [3] ~(first time a lane found the queue empty), [4] ~(kernel start), [5] kernel end
+                                      //     (globaltimer ns; min kept as max of the complement so that memset(0) initialises)
+                                      // [6] number of parked instances, [7] next parked record (phase 2)
+    // tail handling of kernels that support it (Traits::HAS_PARK): see MPC_FISTA.cuh
+    double *park;                     // [PARK_DOUBLES][park_cap] records of parked instances, element-major
+    long long park_cap;
+    int phase;                        // 0: one launch runs every instance to its end
+                                      // 1: park the instances still running `grace` iterations after the queue ran dry
+                                      // 2: resume the parked instances (B is read from queue[6])
+    int grace;
 };
+constexpr int QUEUE_WORDS = 8;
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 
 struct WorkQueue {
     unsigned long long *q;
@@ -142,6 +159,15 @@ struct WorkQueue {
     __device__ __forceinline__ long long next() const {
         unsigned long long i = atomicAdd(q, 1ULL);
         return (i < (unsigned long long)B) ? (long long)i : -1LL;
+    }
+    // launch-shape telemetry (three atomics per warp and launch): when the kernel started, when the queue ran dry (the
+    // start of the tail in which only the slowest instances are still iterating) and when the last warp left
+    __device__ __forceinline__ void mark_start() const {
+        if ((threadIdx.x & 31) == 0) atomicMax(q + 4, ~globaltimer_ns());
+    }
+    __device__ __forceinline__ void mark_drained() const { atomicMax(q + 3, ~globaltimer_ns()); }
+    __device__ __forceinline__ void mark_end() const {
+        if ((threadIdx.x & 31) == 0) atomicMax(q + 5, globaltimer_ns());
     }
 };
 

@@ -59,6 +59,8 @@ struct DeviceCtx {
     int *d_k = nullptr, *d_e = nullptr;
     void *d_scratch = nullptr;   // per-instance state of solvers whose iterates do not fit shared memory
     size_t cap_scratch = 0;
+    double *d_park = nullptr;    // parked-instance records (tail handling, Traits::HAS_PARK)
+    long long cap_park = 0;
 };
 
 template <class Traits> struct Runtime {
@@ -94,10 +96,12 @@ template <class Traits> struct Runtime {
             SPCIES_CK(cudaDeviceGetAttribute(&c.sm_count, cudaDevAttrMultiProcessorCount, dev));
             SPCIES_CK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
             for (auto &e : c.ev) SPCIES_CK(cudaEventCreate(&e));
-            const typename Traits::Consts &hc = Traits::host_consts();
-            SPCIES_CK(cudaMalloc(&c.d_consts, sizeof hc));
-            SPCIES_CK(cudaMemcpy(c.d_consts, &hc, sizeof hc, cudaMemcpyHostToDevice));
-            SPCIES_CK(cudaMalloc(&c.d_queue, 4 * sizeof(unsigned long long)));
+            std::vector<unsigned char> blob(Traits::blob_bytes());
+            Traits::fill_blob(blob.data());
+            SPCIES_CK(cudaMalloc(&c.d_consts, blob.size()));
+            SPCIES_CK(cudaMemcpy(c.d_consts, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+            SPCIES_CK(Traits::init_device_symbols());
+            SPCIES_CK(cudaMalloc(&c.d_queue, QUEUE_WORDS * sizeof(unsigned long long)));
             c.ready = true;
         }
         *out = &c;
@@ -144,7 +148,7 @@ template <class Traits> struct Runtime {
             cudaSetDevice(c.dev);
             cudaFree(c.d_consts); cudaFree(c.d_queue);
             cudaFree(c.d_x0); cudaFree(c.d_xr); cudaFree(c.d_ur); cudaFree(c.d_r); cudaFree(c.d_LB); cudaFree(c.d_UB);
-            cudaFree(c.d_u); cudaFree(c.d_sol); cudaFree(c.d_k); cudaFree(c.d_e); cudaFree(c.d_scratch);
+            cudaFree(c.d_u); cudaFree(c.d_sol); cudaFree(c.d_k); cudaFree(c.d_e); cudaFree(c.d_scratch); cudaFree(c.d_park);
             for (auto &e : c.ev) cudaEventDestroy(e);
             cudaStreamDestroy(c.stream);
             c = DeviceCtx();
@@ -158,6 +162,7 @@ template <class Traits> struct Runtime {
         int *k, *e;
         double *sol;
         int arith, block, grid;
+        int tail_mode, tail_grace;
         bool device_pointers;
         cudaStream_t user_stream;
     };
@@ -166,6 +171,9 @@ template <class Traits> struct Runtime {
         double kernel_ms = 0, h2d_ms = 0, d2h_ms = 0;
         long long sum_k = 0, n_nc = 0;
         int block = 0, grid = 0, smem = 0;
+        int drain_us = 0, span_us = 0;
+        int launches = 0;
+        long long parked = 0;
     };
 
     // one device, one contiguous slice [off, off+B) of the caller's arrays
@@ -212,11 +220,42 @@ template <class Traits> struct Runtime {
             SPCIES_CK(cudaMalloc(&c.d_scratch, need_scratch));
             c.cap_scratch = need_scratch;
         }
-        SPCIES_CK(cudaMemsetAsync(c.d_queue, 0, 4 * sizeof(unsigned long long), s));
+        // tail handling: two launches (park & resume) when the kernel supports it and the batch is larger than one wave
+        bool two_phase = false;
+        if constexpr (Traits::HAS_PARK) {
+            two_phase = cl.tail_mode == SPCIES_CUDA_TAIL_TWO_PHASE ||
+                        (cl.tail_mode == SPCIES_CUDA_TAIL_AUTO && B > 4LL * grid * block);
+            if (two_phase) {
+                const long long need = (long long)grid * block;
+                if (need > c.cap_park) {
+                    if (c.d_park) SPCIES_CK(cudaFree(c.d_park));
+                    c.d_park = nullptr;
+                    SPCIES_CK(cudaMalloc((void **)&c.d_park, (size_t)need * Traits::PARK_DOUBLES * sizeof(double)));
+                    c.cap_park = need;
+                }
+                io.park = c.d_park;
+                io.park_cap = c.cap_park;
+                io.grace = cl.tail_grace > 0 ? cl.tail_grace : 32;
+            }
+        }
+        SPCIES_CK(cudaMemsetAsync(c.d_queue, 0, QUEUE_WORDS * sizeof(unsigned long long), s));
         SPCIES_CK(cudaEventRecord(c.ev[1], s));
-        if (B > 0) SPCIES_CK(Traits::launch(cl.arith, varb, grid, block, smem, s, io, c.d_consts, c.d_scratch));
+        if (B > 0) {
+            io.phase = two_phase ? 1 : 0;
+            SPCIES_CK(Traits::launch(cl.arith, varb, grid, block, smem, s, io, c.d_consts, c.d_scratch));
+            res.launches = 1;
+            if constexpr (Traits::HAS_PARK) {
+                if (two_phase) {
+                    io.phase = 2;
+                    const int block2 = Traits::resume_block(varb);
+                    SPCIES_CK(Traits::launch(cl.arith, varb, c.sm_count, block2, Traits::smem_bytes(block2, varb), s, io, c.d_consts,
+                                             c.d_scratch));
+                    res.launches = 2;
+                }
+            }
+        }
         SPCIES_CK(cudaEventRecord(c.ev[2], s));
-        unsigned long long stats[4] = {0, 0, 0, 0};
+        unsigned long long stats[QUEUE_WORDS] = {0};
         SPCIES_CK(cudaMemcpyAsync(stats, c.d_queue, sizeof stats, cudaMemcpyDeviceToHost, s));
         if (!cl.device_pointers) {
             SPCIES_CK(cudaMemcpyAsync(cl.u, c.d_u, (size_t)B * Traits::MM * 8, cudaMemcpyDeviceToHost, s));
@@ -239,6 +278,12 @@ template <class Traits> struct Runtime {
         }
         res.sum_k = (long long)stats[1];
         res.n_nc = (long long)stats[2];
+        res.parked = (long long)stats[6];
+        if (stats[4] && stats[5]) {
+            const unsigned long long t_start = ~stats[4], t_drain = stats[3] ? ~stats[3] : stats[5];
+            res.span_us = (int)((stats[5] - t_start) / 1000ULL);
+            res.drain_us = (int)((t_drain - t_start) / 1000ULL);
+        }
         res.block = block; res.grid = grid; res.smem = (int)smem;
         return 0;
     }
@@ -277,6 +322,7 @@ template <class Traits> struct Runtime {
             c.u = u + lo * Traits::MM; c.k = k + lo; c.e = e + lo;
             c.sol = sol ? sol + lo * (long long)Traits::SOL_DOUBLES : nullptr;
             c.arith = o.arith; c.block = o.block_threads; c.grid = o.grid_blocks;
+            c.tail_mode = o.tail_mode; c.tail_grace = o.tail_grace;
             c.device_pointers = o.device_pointers != 0;
             c.user_stream = (cudaStream_t)o.stream;
         }
@@ -304,7 +350,10 @@ template <class Traits> struct Runtime {
                 info->d2h_ms = std::max(info->d2h_ms, res[d].d2h_ms);
                 info->sum_k += res[d].sum_k;
                 info->n_not_converged += res[d].n_nc;
-                info->launches += calls[d].B > 0 ? 1 : 0;
+                info->launches += res[d].launches;
+                info->parked += (int)res[d].parked;
+                info->drain_us = std::max(info->drain_us, res[d].drain_us);
+                info->span_us = std::max(info->span_us, res[d].span_us);
             }
             info->block_threads = res[0].block; info->grid_blocks = res[0].grid; info->smem_bytes = res[0].smem;
             info->n_devices = ndev;

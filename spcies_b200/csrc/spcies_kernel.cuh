@@ -77,6 +77,7 @@ __global__ void __launch_bounds__(BLOCK, 1)
     typename S::template Ctx<A, VARB, ST> ctx(C, st, io);
 
     WorkQueue wq{io.queue, io.B};
+    wq.mark_start();
     unsigned long long stat_k = 0;
     unsigned int stat_nc = 0;
     long long inst = -1;
@@ -84,7 +85,10 @@ __global__ void __launch_bounds__(BLOCK, 1)
     for (;;) {
         if (inst < 0) {
             inst = wq.next();
-            if (inst < 0) break;
+            if (inst < 0) {
+                wq.mark_drained();
+                break;
+            }
             ctx.init(inst);
             k = 0;
         }
@@ -99,6 +103,7 @@ __global__ void __launch_bounds__(BLOCK, 1)
         }
     }
     flush_stats(io.queue, stat_k, stat_nc);
+    wq.mark_end();
 }
 
 // Host-side traits for a policy solver
@@ -111,6 +116,12 @@ template <class S> struct PolicyTraits {
     static constexpr int SOL_DOUBLES = (int)(sizeof(SPCIES_SOL_T) / sizeof(double));
     typedef spcies_consts Consts;
     static const Consts &host_consts() { return spcies_h_consts; }
+    static constexpr bool HAS_PARK = false;
+    static constexpr int PARK_DOUBLES = 0;
+    static size_t blob_bytes() { return sizeof(spcies_consts); }
+    static void fill_blob(void *dst) { memcpy(dst, &spcies_h_consts, sizeof spcies_h_consts); }
+    static int resume_block(bool varb) { return default_block(varb); }
+    static cudaError_t init_device_symbols() { return cudaSuccess; }
     static int default_block(bool varb) { return varb ? P::BLOCK_VARB : P::BLOCK_FIXED; }
     static bool gstate(bool varb) { return varb ? P::GSTATE_VARB : P::GSTATE_FIXED; }
     static size_t smem_bytes(int block, bool varb) {

@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 
 from spcies_b200 import prebuilt, sysmodel
-from spcies_b200.solver import ARITH_EXACT, ARITH_FAST
+from spcies_b200.solver import ARITH_EXACT, ARITH_FAST, TAIL_SINGLE, TAIL_TWO_PHASE
 
 pytestmark = pytest.mark.gpu
 
@@ -140,6 +140,54 @@ def test_per_instance_bounds_match_regenerated_reference():
         ur_, kr, er = ref.solve_batch(batch['x0'][idx], batch['xr'][idx], batch['ur'][idx])
         assert np.array_equal(k[idx], kr) and np.array_equal(e[idx], er)
         assert np.array_equal(u[idx], ur_)
+
+
+@pytest.mark.parametrize('name', ['T_laxMPC_FISTA', 'T_equMPC_FISTA', 'C2_laxMPC_FISTA'])
+@pytest.mark.parametrize('grace', [1, 7, 40])
+def test_tail_park_and_resume_is_invisible(name, grace):
+    """Tail handling (two launches: park the instances still iterating `grace` iterations after the queue ran dry,
+    resume them in a second launch): the iterates are copied verbatim, so exact mode stays bit-identical to the
+    reference and to the single-launch run, whatever the parking point."""
+    sol, spec, cfg = prebuilt.get(name)
+    batch, kw = _batch(sol, cfg, 3000, seed=11)
+    ur_, kr, er = _ref(name).solve_batch(batch['x0'], batch['xr'], batch['ur'], threads=8, **kw)
+    u1, k1, e1, i1 = sol.solve_batch(batch['x0'], batch['xr'], batch['ur'], arith=ARITH_EXACT, tail_mode=TAIL_SINGLE)
+    u2, k2, e2, i2 = sol.solve_batch(batch['x0'], batch['xr'], batch['ur'], arith=ARITH_EXACT, tail_mode=TAIL_TWO_PHASE,
+                                     tail_grace=grace)
+    assert i1['launches'] == 1 and i1['parked'] == 0
+    assert i2['launches'] == 2 and i2['parked'] > 0
+    for u, k, e in ((u1, k1, e1), (u2, k2, e2)):
+        assert np.array_equal(e, er) and np.array_equal(k, kr)
+        assert np.array_equal(u.view(np.uint64), ur_.view(np.uint64))
+    assert i2['sum_k'] == int(kr.sum()) and i2['n_not_converged'] == int((er == -1).sum())
+    # fast arithmetic through the same path
+    u3, k3, e3, _ = sol.solve_batch(batch['x0'], batch['xr'], batch['ur'], arith=ARITH_FAST, tail_mode=TAIL_TWO_PHASE,
+                                    tail_grace=grace)
+    assert np.array_equal(e3, er) and np.max(np.abs(k3 - kr)) <= 1
+    same = k3 == kr
+    assert _rel_err(u3[same], ur_[same]) <= 1e-9
+
+
+def test_tail_park_and_resume_with_per_instance_bounds():
+    """Same with opts.LB / UB (the VARB kernels) and the debug payload: two-phase == single launch, bit for bit."""
+    sol, spec, cfg = prebuilt.get('T_laxMPC_FISTA')
+    B = 1500
+    batch = sysmodel.synthetic_batch(cfg['sys'], B, seed=12)
+    rng = np.random.default_rng(5)
+    nm = sol.n + sol.m
+    LB = np.tile(np.concatenate([cfg['sys']['LBx'], cfg['sys']['LBu']]), (B, 1))
+    UB = np.tile(np.concatenate([cfg['sys']['UBx'], cfg['sys']['UBu']]), (B, 1))
+    UB[:, :3] = rng.uniform(0.25, 0.35, size=(B, 3))
+    LB[:, sol.n:] = -rng.uniform(0.5, 0.8, size=(B, sol.m))
+    assert LB.shape == (B, nm)
+    a = sol.solve_batch(batch['x0'], batch['xr'], batch['ur'], LB=LB, UB=UB, arith=ARITH_EXACT, tail_mode=TAIL_SINGLE,
+                        want_sol=True)
+    b = sol.solve_batch(batch['x0'], batch['xr'], batch['ur'], LB=LB, UB=UB, arith=ARITH_EXACT, tail_mode=TAIL_TWO_PHASE,
+                        tail_grace=5, want_sol=True)
+    assert b[3]['parked'] > 0
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    for f, _len in spec.sol_fields:
+        assert np.array_equal(a[4][f], b[4][f]), f
 
 
 def test_empty_and_ragged_batches():

@@ -400,8 +400,8 @@ __global__ void __launch_bounds__(BLOCK, 1) fista_kernel(const BatchIO io, const
     const real tol_ = (real)tol;
     const bool resume = io.phase == 2;
     const long long B = resume ? (long long)io.queue[6] : io.B;
-    const WorkQueue wq{resume ? io.queue + 7 : io.queue, B};
-    const WorkQueue marks{io.queue, B};
+    const WorkQueue wq{resume ? io.queue + 7 : io.queue, B, resume ? nullptr : io.ready};
+    const WorkQueue marks{io.queue, B, nullptr};
     marks.mark_start();
     unsigned long long stat_k = 0;
     unsigned int stat_nc = 0;

@@ -144,8 +144,10 @@ struct BatchIO {
                                       // 1: park the instances still running `grace` iterations after the queue ran dry
                                       // 2: resume the parked instances (B is read from queue[6])
     int grace;
+    const unsigned long long *ready;  // optional: instances [0, *ready) have their inputs in device memory (the host->device
+                                      // copies of a host-buffer call run on a second stream, chunk by chunk, under the kernel)
 };
-constexpr int QUEUE_WORDS = 8;
+constexpr int QUEUE_WORDS = 16;   // [8]: number of instances whose inputs have arrived (pipelined host->device copies)
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;
@@ -156,9 +158,14 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 struct WorkQueue {
     unsigned long long *q;
     long long B;
+    const unsigned long long *ready = nullptr;
     __device__ __forceinline__ long long next() const {
         unsigned long long i = atomicAdd(q, 1ULL);
-        return (i < (unsigned long long)B) ? (long long)i : -1LL;
+        if (i >= (unsigned long long)B) return -1LL;
+        if (ready) {   // inputs still in flight: wait for the watermark (chunk boundaries never share a cache line)
+            while (*(const volatile unsigned long long *)ready <= i) __nanosleep(500);
+        }
+        return (long long)i;
     }
     // launch-shape telemetry (three atomics per warp and launch): when the kernel started, when the queue ran dry (the
     // start of the tail in which only the slowest instances are still iterating) and when the last warp left

@@ -44,11 +44,15 @@ static inline int fail(int code, const char *what) {
         if (_e != cudaSuccess) return ::spcies::fail((int)_e, #call); \
     } while (0)
 
+constexpr int MAX_CHUNKS = 32;
+
 struct DeviceCtx {
     int dev = -1;
     bool ready = false;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;          // host->device input chunks, overlapped with the solver kernel
+    unsigned long long *h_ready = nullptr;       // pinned: watermark values copied to d_queue[8] after every chunk
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     void *d_consts = nullptr;
     unsigned long long *d_queue = nullptr;
@@ -95,6 +99,8 @@ template <class Traits> struct Runtime {
             c.dev = dev;
             SPCIES_CK(cudaDeviceGetAttribute(&c.sm_count, cudaDevAttrMultiProcessorCount, dev));
             SPCIES_CK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+            SPCIES_CK(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+            SPCIES_CK(cudaHostAlloc((void **)&c.h_ready, MAX_CHUNKS * sizeof(unsigned long long), cudaHostAllocDefault));
             for (auto &e : c.ev) SPCIES_CK(cudaEventCreate(&e));
             std::vector<unsigned char> blob(Traits::blob_bytes());
             Traits::fill_blob(blob.data());
@@ -151,6 +157,8 @@ template <class Traits> struct Runtime {
             cudaFree(c.d_u); cudaFree(c.d_sol); cudaFree(c.d_k); cudaFree(c.d_e); cudaFree(c.d_scratch); cudaFree(c.d_park);
             for (auto &e : c.ev) cudaEventDestroy(e);
             cudaStreamDestroy(c.stream);
+            cudaStreamDestroy(c.copy_stream);
+            cudaFreeHost(c.h_ready);
             c = DeviceCtx();
         }
     }
@@ -195,15 +203,6 @@ template <class Traits> struct Runtime {
             io.u = cl.u; io.k = cl.k; io.e = cl.e; io.sol = cl.sol;
         } else {
             if ((rc = reserve(c, B, varb, cl.sol != nullptr))) return rc;
-            SPCIES_CK(cudaEventRecord(c.ev[0], s));
-            SPCIES_CK(cudaMemcpyAsync(c.d_x0, cl.x0, (size_t)B * Traits::NN * 8, cudaMemcpyHostToDevice, s));
-            SPCIES_CK(cudaMemcpyAsync(c.d_xr, cl.xr, (size_t)B * Traits::NN * 8, cudaMemcpyHostToDevice, s));
-            SPCIES_CK(cudaMemcpyAsync(c.d_ur, cl.ur, (size_t)B * Traits::MM * 8, cudaMemcpyHostToDevice, s));
-            if (Traits::HAS_R) SPCIES_CK(cudaMemcpyAsync(c.d_r, cl.r, (size_t)B * 8, cudaMemcpyHostToDevice, s));
-            if (varb) {
-                SPCIES_CK(cudaMemcpyAsync(c.d_LB, cl.LB, (size_t)B * Traits::NMM * 8, cudaMemcpyHostToDevice, s));
-                SPCIES_CK(cudaMemcpyAsync(c.d_UB, cl.UB, (size_t)B * Traits::NMM * 8, cudaMemcpyHostToDevice, s));
-            }
             io.x0 = c.d_x0; io.xr = c.d_xr; io.ur = c.d_ur; io.r = c.d_r;
             io.LB = varb ? c.d_LB : nullptr; io.UB = varb ? c.d_UB : nullptr;
             io.u = c.d_u; io.k = c.d_k; io.e = c.d_e; io.sol = cl.sol ? c.d_sol : nullptr;
@@ -239,6 +238,42 @@ template <class Traits> struct Runtime {
             }
         }
         SPCIES_CK(cudaMemsetAsync(c.d_queue, 0, QUEUE_WORDS * sizeof(unsigned long long), s));
+        bool pipelined = false;
+        if (!cl.device_pointers) {
+            // host -> device.  Large batches: chunk by chunk on the copy stream, under the kernel; a watermark word tells
+            // the kernel how many instances have arrived (first chunk = two waves of lanes, so the kernel starts at once).
+            // Chunks are multiples of 32 instances: no 128-byte line is shared between two chunks.
+            pipelined = B >= 8LL * grid * block;
+            cudaStream_t cs = pipelined ? c.copy_stream : s;
+            if (pipelined) {
+                SPCIES_CK(cudaEventRecord(c.ev[5], s));
+                SPCIES_CK(cudaStreamWaitEvent(cs, c.ev[5], 0));
+            }
+            SPCIES_CK(cudaEventRecord(c.ev[0], cs));
+            long long first = pipelined ? ((2LL * grid * block + 31) / 32 * 32) : B;
+            long long rest = pipelined ? (((B - first) / (MAX_CHUNKS / 2 - 1) + 31) / 32 * 32) : 0;
+            if (rest < 32) rest = 32;
+            int nchunk = 0;
+            for (long long lo = 0; lo < B; ++nchunk) {
+                const long long hi = std::min<long long>(B, lo + (nchunk == 0 ? first : rest));
+                const size_t cnt = (size_t)(hi - lo);
+                SPCIES_CK(cudaMemcpyAsync(c.d_x0 + lo * Traits::NN, cl.x0 + lo * Traits::NN, cnt * Traits::NN * 8, cudaMemcpyHostToDevice, cs));
+                SPCIES_CK(cudaMemcpyAsync(c.d_xr + lo * Traits::NN, cl.xr + lo * Traits::NN, cnt * Traits::NN * 8, cudaMemcpyHostToDevice, cs));
+                SPCIES_CK(cudaMemcpyAsync(c.d_ur + lo * Traits::MM, cl.ur + lo * Traits::MM, cnt * Traits::MM * 8, cudaMemcpyHostToDevice, cs));
+                if (Traits::HAS_R) SPCIES_CK(cudaMemcpyAsync(c.d_r + lo, cl.r + lo, cnt * 8, cudaMemcpyHostToDevice, cs));
+                if (varb) {
+                    SPCIES_CK(cudaMemcpyAsync(c.d_LB + lo * Traits::NMM, cl.LB + lo * Traits::NMM, cnt * Traits::NMM * 8, cudaMemcpyHostToDevice, cs));
+                    SPCIES_CK(cudaMemcpyAsync(c.d_UB + lo * Traits::NMM, cl.UB + lo * Traits::NMM, cnt * Traits::NMM * 8, cudaMemcpyHostToDevice, cs));
+                }
+                if (pipelined) {
+                    c.h_ready[nchunk] = (unsigned long long)hi;
+                    SPCIES_CK(cudaMemcpyAsync(c.d_queue + 8, c.h_ready + nchunk, sizeof(unsigned long long), cudaMemcpyHostToDevice, cs));
+                }
+                lo = hi;
+            }
+            SPCIES_CK(cudaEventRecord(c.ev[4], cs));
+            if (pipelined) io.ready = c.d_queue + 8;
+        }
         SPCIES_CK(cudaEventRecord(c.ev[1], s));
         if (B > 0) {
             io.phase = two_phase ? 1 : 0;
@@ -255,6 +290,7 @@ template <class Traits> struct Runtime {
             }
         }
         SPCIES_CK(cudaEventRecord(c.ev[2], s));
+        if (pipelined) SPCIES_CK(cudaStreamWaitEvent(s, c.ev[4], 0));
         unsigned long long stats[QUEUE_WORDS] = {0};
         SPCIES_CK(cudaMemcpyAsync(stats, c.d_queue, sizeof stats, cudaMemcpyDeviceToHost, s));
         if (!cl.device_pointers) {
@@ -271,7 +307,7 @@ template <class Traits> struct Runtime {
         SPCIES_CK(cudaEventElapsedTime(&ms, c.ev[1], c.ev[2]));
         res.kernel_ms = ms;
         if (!cl.device_pointers) {
-            SPCIES_CK(cudaEventElapsedTime(&ms, c.ev[0], c.ev[1]));
+            SPCIES_CK(cudaEventElapsedTime(&ms, c.ev[0], c.ev[4]));
             res.h2d_ms = ms;
             SPCIES_CK(cudaEventElapsedTime(&ms, c.ev[2], c.ev[3]));
             res.d2h_ms = ms;

@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(BLOCK, 1)
     }
     typename S::template Ctx<A, VARB, ST> ctx(C, st, io);
 
-    WorkQueue wq{io.queue, io.B};
+    WorkQueue wq{io.queue, io.B, io.ready};
     wq.mark_start();
     unsigned long long stat_k = 0;
     unsigned int stat_nc = 0;

@@ -190,6 +190,27 @@ def test_tail_park_and_resume_with_per_instance_bounds():
         assert np.array_equal(a[4][f], b[4][f]), f
 
 
+def test_large_host_batch_pipelined_copies_and_auto_tail():
+    """A host-buffer call large enough for the pipelined host->device copies (chunks arrive under the running kernel,
+    the queue waits on the watermark) and for the automatic two-launch tail handling: exact mode, checked against the
+    reference on the first / last / a random subset of the instances, and against a device-resident single-launch run
+    of the whole batch through the checksum of all outputs."""
+    sol, spec, cfg = prebuilt.get('C2_laxMPC_FISTA')
+    B = 330_000
+    batch = sysmodel.synthetic_batch(cfg['sys'], B, seed=21)
+    u, k, e, info = sol.solve_batch(batch['x0'], batch['xr'], batch['ur'], arith=ARITH_EXACT)
+    assert info['launches'] == 2 and info['parked'] > 0
+    rng = np.random.default_rng(3)
+    idx = np.unique(np.concatenate([np.arange(3000), np.arange(B - 3000, B), rng.integers(0, B, 6000)]))
+    ur_, kr, er = _ref('C2_laxMPC_FISTA').solve_batch(batch['x0'][idx], batch['xr'][idx], batch['ur'][idx], threads=16)
+    assert np.array_equal(k[idx], kr) and np.array_equal(e[idx], er)
+    assert np.array_equal(u[idx].view(np.uint64), ur_.view(np.uint64))
+    u1, k1, e1, info1 = sol.solve_batch(batch['x0'], batch['xr'], batch['ur'], arith=ARITH_EXACT, tail_mode=TAIL_SINGLE)
+    assert info1['launches'] == 1
+    assert np.array_equal(u.view(np.uint64), u1.view(np.uint64)) and np.array_equal(k, k1) and np.array_equal(e, e1)
+    assert info['sum_k'] == int(k.sum()) == info1['sum_k']
+
+
 def test_empty_and_ragged_batches():
     sol, spec, cfg = prebuilt.get('C2_laxMPC_FISTA')
     for B in (0, 1, 31, 33, 127, 129, 1000):

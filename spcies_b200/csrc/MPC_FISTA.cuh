@@ -72,6 +72,13 @@
 #ifndef SPCIES_FISTA_BLOCK2
 #define SPCIES_FISTA_BLOCK2 128      // threads per CTA of the tail launch (one warp per scheduler)
 #endif
+#ifndef SPCIES_FISTA_COOP
+#define SPCIES_FISTA_COOP 0          // 1: the tail launch of FAST-mode calls uses the cooperative kernel (MPC_FISTA_coop.cuh); measured slower
+                                     // than the one-thread-per-instance tail (shared-memory wavefront bound), kept as an experiment
+#endif
+#ifndef SPCIES_FISTA_TAIL_TMEM
+#define SPCIES_FISTA_TAIL_TMEM 0     // 1: the tail launch keeps lambda / w in Tensor Memory as well (fewer shared-memory wavefronts)
+#endif
 #ifndef SPCIES_FISTA_CBANK
 #define SPCIES_FISTA_CBANK 0         // 1: QRi / LB / UB operands through the constant bank instead of shared memory
 #endif
@@ -176,7 +183,7 @@ static_assert(block_sm(true) >= 32 || USE_TMEM, "per-instance state does not fit
 constexpr int BLOCK1_FIXED = USE_TMEM ? block_tm(false) : block_sm(false);
 constexpr int BLOCK1_VARB = USE_TMEM ? block_tm(true) : block_sm(true);
 // tail configuration (second launch): all iterates in shared memory when that fits, at most BLOCK2 threads
-constexpr bool TAIL_TMEM = USE_TMEM && block_sm(true) < 32;
+constexpr bool TAIL_TMEM = USE_TMEM && (block_sm(true) < 32 || SPCIES_FISTA_TAIL_TMEM != 0);
 constexpr int block_tail(bool varb) {
     int t = TAIL_TMEM ? block_tm(varb) : block_sm(varb);
     return t > SPCIES_FISTA_BLOCK2 ? SPCIES_FISTA_BLOCK2 : t;
@@ -702,6 +709,8 @@ __global__ void __launch_bounds__(BLOCK, 1) fista_kernel(const BatchIO io, const
     if constexpr (TM) tmem::free_all(tbase);
 }
 
+#include "MPC_FISTA_coop.cuh"
+
 struct Traits {
     static constexpr int NN = n, MM = m, NMM = nm;
     static constexpr bool HAS_R = false;
@@ -756,9 +765,21 @@ struct Traits {
         return cudaErrorInvalidConfiguration;
     }
     static size_t scratch_bytes(int, int, bool) { return 0; }
+    template <bool VARB>
+    static cudaError_t launch_coop(int grid, cudaStream_t s, const BatchIO &io, const void *dc) {
+        auto kern = fista_coop_kernel<VARB>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COOP_SMEM);
+        if (e != cudaSuccess) return e;
+        kern<<<grid, COOP_BLOCK, COOP_SMEM, s>>>(io, (const spcies_consts *)dc);
+        return cudaGetLastError();
+    }
     static cudaError_t launch(int arith, bool varb, int grid, int block, size_t smem, cudaStream_t s, const BatchIO &io,
                               const void *dc, void *) {
         const bool ex = arith == SPCIES_CUDA_ARITH_EXACT;
+        if constexpr (HAS_COOP && SPCIES_FISTA_COOP != 0) {
+            // tail launch, FAST arithmetic, no debug payload: eight lanes per instance
+            if (io.phase == 2 && !ex && io.sol == nullptr) return varb ? launch_coop<true>(grid, s, io, dc) : launch_coop<false>(grid, s, io, dc);
+        }
         if (varb) return ex ? launch_b<true, true>(grid, block, smem, s, io, dc) : launch_b<false, true>(grid, block, smem, s, io, dc);
         return ex ? launch_b<true, false>(grid, block, smem, s, io, dc) : launch_b<false, false>(grid, block, smem, s, io, dc);
     }

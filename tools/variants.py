@@ -68,9 +68,12 @@ def run(B):
         u, k, e, info = sol.solve_batch(small['x0'], small['xr'], small['ur'], arith=ARITH_FAST, tail_mode=2, tail_grace=3)
         same = k == kr
         relerr = float((np.abs(u[same] - ur_[same]) / np.maximum(1.0, np.abs(ur_[same]))).max())
-        fast = dict(e_same=bool(np.array_equal(e, er)), max_dk=int(np.abs(k - kr).max()), n_dk=int((~same).sum()), u_rel=relerr)
+        u1, k1, e1, _ = sol.solve_batch(small['x0'], small['xr'], small['ur'], arith=ARITH_FAST, tail_mode=1)
+        fast = dict(e_same=bool(np.array_equal(e, er)), max_dk=int(np.abs(k - kr).max()), n_dk=int((~same).sum()), u_rel=relerr,
+                    two_phase_same_bits=bool(np.array_equal(u.view(np.uint64), u1.view(np.uint64)) and np.array_equal(k, k1)),
+                    parked=info['parked'])
         out[name] = dict(exact=exact, exact_two_phase=exact2, parked_small=parked_small, fast=fast, runs={})
-        for mode, grace in ((1, 0), (0, 32), (0, 8), (0, 64)):
+        for mode, grace in ((1, 0), (0, 32), (0, 16), (0, 64), (0, 128)):
             ms = []
             for i in range(4):
                 info = sol.solve_batch_device(B, d['x0'].data_ptr(), d['xr'].data_ptr(), d['ur'].data_ptr(), d_u.data_ptr(),

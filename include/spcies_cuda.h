@@ -62,6 +62,17 @@ extern "C" {
 #define SPCIES_CUDA_TAIL_AUTO   0
 #define SPCIES_CUDA_TAIL_SINGLE 1  /* always one launch that runs every instance to its end */
 #define SPCIES_CUDA_TAIL_TWO_PHASE 2 /* always park & resume (AUTO does so for batches larger than four waves of lanes) */
+#define SPCIES_CUDA_TAIL_CAPS   3  /* iteration-cap rounds (MMA engine; AUTO uses them for large batches): launch r runs every
+                                    * instance it holds up to tail_caps[r] iterations and parks the rest for launch r+1, the last
+                                    * launch runs what is left to the end.  Slow instances are thus found -- and restarted together --
+                                    * early, instead of trailing the launch one by one.  Falls back to TWO_PHASE on other engines. */
+
+/* Kernel engine of the FISTA solvers (FAST arithmetic only; every other solver has one engine and ignores the field).
+ * MMA: FP64 tensor-core kernel, 8 instances per warp, iterates in registers, shared matrices as MMA fragments.
+ * SCALAR: one thread per instance.  AUTO picks MMA when the problem fits it (nn_ + mm_ <= 8, N <= 12, double). */
+#define SPCIES_CUDA_ENGINE_AUTO   0
+#define SPCIES_CUDA_ENGINE_SCALAR 1
+#define SPCIES_CUDA_ENGINE_MMA    2  /* fail with cudaErrorNotSupported instead of falling back to SCALAR */
 
 /* Options of a batched call.  Zero-initialise, then set what you need; NULL means all defaults. */
 typedef struct {
@@ -76,7 +87,9 @@ typedef struct {
     int grid_blocks;         /* 0: one CTA per SM */
     int tail_mode;           /* SPCIES_CUDA_TAIL_AUTO (default) | _SINGLE | _TWO_PHASE, see above */
     int tail_grace;          /* iterations an instance may still run after the queue ran dry before it is parked (0: 32) */
-    int reserved[6];
+    int engine;              /* SPCIES_CUDA_ENGINE_AUTO (default) | _SCALAR | _MMA, see above */
+    int tail_caps[3];        /* increasing iteration caps of SPCIES_CUDA_TAIL_CAPS, 0-terminated (all 0: 96, 320) */
+    int reserved[2];
 } spcies_batch_opts;
 
 /* Measurements of the last batched call (all device times from CUDA events on the launching stream). */

@@ -710,6 +710,7 @@ __global__ void __launch_bounds__(BLOCK, 1) fista_kernel(const BatchIO io, const
 }
 
 #include "MPC_FISTA_coop.cuh"
+#include "MPC_FISTA_mma.cuh"
 
 struct Traits {
     static constexpr int NN = n, MM = m, NMM = nm;
@@ -717,18 +718,40 @@ struct Traits {
     static constexpr bool HAS_VARB = true;
     static constexpr bool HAS_PARK = true;                   // phase-1 / phase-2 launches (park & resume the slow tail)
     static constexpr int PARK_DOUBLES = fista::PARK_DOUBLES;
+    static constexpr int K_MAX = k_max;
     static constexpr int SOL_DOUBLES = (int)(sizeof(SPCIES_SOL_T) / sizeof(double));
     typedef spcies_consts Consts;
     static const Consts &host_consts() { return spcies_h_consts; }
     // device constant blob: the generated constants + the derived FAST-mode blocks
-    static size_t blob_bytes() { return BLOB_BYTES; }
+    static size_t blob_bytes() { return HAS_MMA ? TOTAL_BLOB_BYTES : BLOB_BYTES; }
     static void fill_blob(void *dst) {
-        memset(dst, 0, BLOB_BYTES);
+        memset(dst, 0, blob_bytes());
         memcpy(dst, &spcies_h_consts, sizeof spcies_h_consts);
         FistaDerived *D = new FistaDerived;
         compute_derived(spcies_h_consts, *D);
         memcpy((char *)dst + CONSTS_BYTES, D, sizeof *D);
+        if constexpr (HAS_MMA) {
+            MmaTables *T = new MmaTables;
+            fill_mma_tables(spcies_h_consts, *D, *T);
+            memcpy((char *)dst + MMA_OFFSET, T, sizeof *T);
+            delete T;
+        }
         delete D;
+    }
+    // which engine runs a call: the tensor-core kernel for FAST arithmetic without debug payload, unless the caller
+    // asked for the scalar one (spcies_batch_opts.engine)
+    static bool use_mma(int arith, const BatchIO &io) {
+        if constexpr (!HAS_MMA) return false;
+        return arith != SPCIES_CUDA_ARITH_EXACT && io.sol == nullptr && io.engine != SPCIES_CUDA_ENGINE_SCALAR;
+    }
+    static bool caps_engine(int arith, const BatchIO &io) { return use_mma(arith, io); }   // iteration-cap rounds
+    static void engine_shape(int arith, const BatchIO &io, int &block, size_t &smem, int &ipb) {
+        ipb = block;
+        if (use_mma(arith, io)) {
+            block = MMA_BLOCK;
+            smem = MMA_BYTES;
+            ipb = MMA_IPB;
+        }
     }
     static cudaError_t init_device_symbols() {
 #if SPCIES_FISTA_CBANK
@@ -776,6 +799,16 @@ struct Traits {
     static cudaError_t launch(int arith, bool varb, int grid, int block, size_t smem, cudaStream_t s, const BatchIO &io,
                               const void *dc, void *) {
         const bool ex = arith == SPCIES_CUDA_ARITH_EXACT;
+        if (io.engine == SPCIES_CUDA_ENGINE_MMA && !use_mma(arith, io)) return cudaErrorNotSupported;
+        if constexpr (HAS_MMA) {
+            if (use_mma(arith, io)) {
+                auto kern = varb ? fista_mma_kernel<true> : fista_mma_kernel<false>;
+                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MMA_BYTES);
+                if (e != cudaSuccess) return e;
+                kern<<<grid, MMA_BLOCK, MMA_BYTES, s>>>(io, (const unsigned char *)dc);
+                return cudaGetLastError();
+            }
+        }
         if constexpr (HAS_COOP && SPCIES_FISTA_COOP != 0) {
             // tail launch, FAST arithmetic, no debug payload: eight lanes per instance
             if (io.phase == 2 && !ex && io.sol == nullptr) return varb ? launch_coop<true>(grid, s, io, dc) : launch_coop<false>(grid, s, io, dc);
@@ -785,6 +818,9 @@ struct Traits {
     }
     static cudaError_t attributes(int arith, bool varb, cudaFuncAttributes *a) {
         const bool ex = arith == SPCIES_CUDA_ARITH_EXACT;
+        if constexpr (HAS_MMA) {
+            if (!ex) return varb ? cudaFuncGetAttributes(a, fista_mma_kernel<true>) : cudaFuncGetAttributes(a, fista_mma_kernel<false>);
+        }
         if (varb)
             return ex ? cudaFuncGetAttributes(a, fista_kernel<true, true, BLOCK1_VARB, USE_TMEM>)
                       : cudaFuncGetAttributes(a, fista_kernel<false, true, BLOCK1_VARB, USE_TMEM>);

@@ -1,0 +1,418 @@
+// MPC_FISTA_mma.cuh -- tensor-core (DMMA) engine of the FISTA solver (included by MPC_FISTA.cuh, inside spcies::fista).
+//
+// Why.  ncu on the one-thread-per-instance kernel (profiles/r1_fista_v3_ncu_summary.txt) shows the batched
+// shared-matrix block products as the bottleneck: every DFMA of the W-solve takes a warp-uniform constant that costs
+// one shared-memory wavefront per 8 bytes (shared pipe 69 % busy, FP64 pipe 55 %), the per-instance iterates (200
+// doubles) do not fit the register file, and the ~5200-instruction iteration of one thread makes the tail of the
+// slowest instances latency bound (5.6 ms of a 13.9 ms step).  Every product of the FAST arithmetic is a dense
+// (<= 8 x 8) shared matrix times a per-instance vector, i.e. one small GEMM per warp with the batch as the M dimension.
+//
+// Mapping.  A warp owns 8 instances (one per row of the m8n8k4 FP64 MMA, SASS DMMA.8x8x4); the 4 lanes of a lane group
+// hold the instance's vectors, 2 components per lane: lane (g = lane / 4, t = lane % 4) holds components 2t and 2t+1 of
+// every vector of instance g.  That is exactly the C/D fragment layout, and -- with the shared matrix's columns split
+// even / odd over two MMAs -- also the A fragment layout, so products chain with no shuffle:
+//
+//     v' = c + M v :   D = A0 * B0 + C,  D = A1 * B1 + D      A0[g][t] = v_g[2t], A1[g][t] = v_g[2t+1]   (registers of v)
+//                                                              B0[t][o] = M[o][2t], B1[t][o] = M[o][2t+1] (lane reads the
+//                                                              double2 at index `lane` of the row-major 8 x 8 M)
+//
+// All iterates (y, lambda, w: 3 N vectors = 60 doubles per lane at N = 10) and the [A B] fragments live in registers; the
+// 4 N stage matrices (Linv, -F, Uinv, -G) are read from shared memory as one conflict-free LDS.128 per lane and matrix
+// (4 wavefronts per 8 instances instead of 36 per 32).  116 DMMA per warp iteration (N = 10); the component-wise work
+// (scaling, clipping, exit test, momentum) is 2 components per lane.  The t-sequence of FISTA does not depend on the
+// instance, so the momentum coefficient (t_{k-1} - 1) / t_k is a table indexed by k (no sqrt / divide in the loop).
+//
+// Arithmetic: the FAST arithmetic of fista_kernel (explicit block inverses, FMA) with the dot products accumulated in
+// the MMA's order; results differ from the reference by rounding only (same gate: u_opt <= 1e-9 relative, e_flag
+// identical, |dk| <= 1).  EXACT mode, float precision, the debug payload and problems with nn_ + mm_ > 8 use the
+// one-thread-per-instance kernel.  Refill is per lane group; park & resume (io.phase) use the same record format.
+#pragma once
+
+#ifndef SPCIES_FISTA_MMA
+#define SPCIES_FISTA_MMA 1           // 0: never use the tensor-core engine
+#endif
+#ifndef SPCIES_FISTA_MMA_PRESCALE
+#define SPCIES_FISTA_MMA_PRESCALE 1  // 1: fold the QRi / Ti scalings of z into [A B]' and q (one FP64 operation less per component of z;
+                                     // the constants are rounded once more: same measured accuracy, tools/diag_equ.py)
+#endif
+#ifndef SPCIES_FISTA_MMA_BLOCK
+#define SPCIES_FISTA_MMA_BLOCK 256
+#endif
+
+constexpr int MMA_BLOCK = SPCIES_FISTA_MMA_BLOCK;
+constexpr int MMA_IPB = MMA_BLOCK / 4;                    // instances resident per CTA
+constexpr bool HAS_MMA = SPCIES_FISTA_MMA != 0 && sizeof(real) == 8 && nm <= 8 && N >= 2 && N <= 12;
+constexpr int MMA_KTAB = k_max + 2;
+constexpr bool PRESCALE = SPCIES_FISTA_MMA_PRESCALE != 0;
+
+struct alignas(16) MmaTables {
+    double SNABt[64];         // -[A B]'  (out nm, in n)   [PRESCALE: -diag(QRi) [A B]', the scaling of z folded into the product]
+    double NAB[64];           // -[A B]   (out n, in nm)
+    double Linv[N][64], NF[N][64], Uinv[N][64], NG[N][64];
+    double QRi[8], Ti[8];     // component scalings (stored negated by the generator, like Q, R, T)
+    double Qs[8], Ts[8];      // q = Qs o [xr; ur],  qT = Ts o xr (lax) | xr (equ)   [PRESCALE: times QRi, Ti]
+    double LBs[N + 1][8];     // row 0: u_0 (components n..nm-1), rows 1..N-1: stage l = row - 1, row N: terminal state
+    double UBs[N + 1][8];
+    double beta[MMA_KTAB];    // momentum coefficient of the pass that follows the k-th exit test (0 for k = 0, 1)
+};
+constexpr size_t MMA_BYTES = (sizeof(MmaTables) + 15) / 16 * 16;
+constexpr size_t MMA_OFFSET = BLOB_BYTES;                 // position in the device constant blob
+constexpr size_t TOTAL_BLOB_BYTES = BLOB_BYTES + MMA_BYTES;
+
+static inline void fill_mma_tables(const spcies_consts &C, const FistaDerived &D, MmaTables &T) {
+    memset(&T, 0, sizeof T);
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < nm; ++j) {
+            T.SNABt[j * 8 + i] = PRESCALE ? -(double)C.QRi[j] * (double)C.AB[i][j] : -(double)C.AB[i][j];
+            T.NAB[i * 8 + j] = -(double)C.AB[i][j];
+        }
+    for (int l = 0; l < N; ++l)
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < n; ++j) {
+                T.Linv[l][i * 8 + j] = (double)D.Linv[l][i][j];
+                T.NF[l][i * 8 + j] = -(double)D.F[l][i][j];
+                T.Uinv[l][i * 8 + j] = (double)D.Uinv[l][i][j];
+                T.NG[l][i * 8 + j] = -(double)D.G[l][i][j];
+            }
+    for (int e = 0; e < nm; ++e) T.QRi[e] = (double)C.QRi[e];
+    for (int e = 0; e < n; ++e) {
+        T.Qs[e] = PRESCALE ? (double)C.QRi[e] * (double)C.Q[e] : (double)C.Q[e];
+#if SPCIES_TERMINAL
+        T.Ti[e] = (double)C.Ti[e];
+        T.Ts[e] = PRESCALE ? (double)C.Ti[e] * (double)C.T[e] : (double)C.T[e];
+#else
+        T.Ts[e] = 1.0;
+#endif
+    }
+    for (int j = 0; j < m; ++j) T.Qs[n + j] = PRESCALE ? (double)C.QRi[n + j] * (double)C.R[j] : (double)C.R[j];
+    for (int s = 0; s <= N; ++s)
+        for (int e = 0; e < 8; ++e) {
+            T.LBs[s][e] = -1e300;
+            T.UBs[s][e] = 1e300;
+        }
+#ifdef VAR_BOUNDS
+    for (int j = 0; j < m; ++j) {
+        T.LBs[0][n + j] = (double)C.LB0[j];
+        T.UBs[0][n + j] = (double)C.UB0[j];
+    }
+    for (int l = 0; l < N - 1; ++l)
+        for (int e = 0; e < nm; ++e) {
+            T.LBs[l + 1][e] = (double)C.LB[l][e];
+            T.UBs[l + 1][e] = (double)C.UB[l][e];
+        }
+#if SPCIES_TERMINAL
+    for (int e = 0; e < n; ++e) {
+        T.LBs[N][e] = (double)C.LBN[e];
+        T.UBs[N][e] = (double)C.UBN[e];
+    }
+#endif
+#else
+    for (int s = 0; s <= N; ++s)
+        for (int e = 0; e < nm; ++e) {
+            T.LBs[s][e] = (double)C.LB[e];
+            T.UBs[s][e] = (double)C.UB[e];
+        }
+#endif
+    // t_0 = 1;  t_k = (1 + sqrt(1 + 4 t_{k-1}^2)) / 2;  beta_k = (t_{k-1} - 1) / t_k      code_laxMPC_FISTA_C.c:370-385
+    volatile double t = 1.0;
+    T.beta[0] = 0.0;
+    for (int k = 1; k < MMA_KTAB; ++k) {
+        const double t1 = t;
+        volatile double s = 4.0 * t1;
+        s = s * t1;
+        s = 1.0 + s;
+        t = 0.5 * (1.0 + sqrt(s));
+        T.beta[k] = (t1 - 1.0) / t;
+    }
+}
+
+// D = A B + C on one k-step (4 components) of the 8 instances of the warp
+__device__ __forceinline__ void dmma(double &d0, double &d1, const double a, const double b, const double c0, const double c1) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};\n"
+                 : "=d"(d0), "=d"(d1)
+                 : "d"(a), "d"(b), "d"(c0), "d"(c1));
+}
+// out = c + M v   (M = the lane's double2 of the row-major 8 x 8 matrix; out may alias c)
+__device__ __forceinline__ void mma_mv(double (&out)[2], const double2 M, const double (&v)[2], const double c0, const double c1) {
+    double e0, e1;
+    dmma(e0, e1, v[0], M.x, c0, c1);
+    dmma(out[0], out[1], v[1], M.y, e0, e1);
+}
+__device__ __forceinline__ double2 mma_mat(const double *M, int lane) { return reinterpret_cast<const double2 *>(M)[lane]; }
+
+template <bool VARB>
+__global__ void __launch_bounds__(MMA_BLOCK, 1) fista_mma_kernel(const BatchIO io, const unsigned char *__restrict__ g_blob) {
+    constexpr unsigned FULL = 0xffffffffu;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ uint64_t mbar;
+    const MmaTables *T = reinterpret_cast<const MmaTables *>(smem_raw);
+    stage_constants(smem_raw, g_blob + MMA_OFFSET, (uint32_t)MMA_BYTES, &mbar);
+
+    const int lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
+    const int ec[2] = {2 * t4, 2 * t4 + 1};                       // the two vector components of this lane
+    const bool xs[2] = {ec[0] < n, ec[1] < n};                    // state component
+    const bool us[2] = {ec[0] >= n && ec[0] < nm, ec[1] >= n && ec[1] < nm};   // input component
+    const unsigned gmask = 0xFu << (4 * g);
+    const bool leader = t4 == 0;
+
+    const double2 nabt = mma_mat(T->SNABt, lane), nab = mma_mat(T->NAB, lane);
+    double qri[2], qs[2], ts[2], lb[2], ub[2];
+#if SPCIES_TERMINAL
+    double ti[2];
+#endif
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        qri[i] = T->QRi[ec[i]];
+        qs[i] = T->Qs[ec[i]];
+        ts[i] = T->Ts[ec[i]];
+#if SPCIES_TERMINAL
+        ti[i] = T->Ti[ec[i]];
+#endif
+        lb[i] = T->LBs[1][ec[i]];
+        ub[i] = T->UBs[1][ec[i]];
+    }
+    // bounds of stage row s (0: u_0, 1..N-1: stage s-1, N: terminal)
+    auto bnd = [&](int s, int i, double &lo, double &hi) {
+#ifdef VAR_BOUNDS
+        if (!VARB) {
+            lo = T->LBs[s][ec[i]];
+            hi = T->UBs[s][ec[i]];
+            return;
+        }
+#endif
+        lo = lb[i];
+        hi = ub[i];
+    };
+
+    const double tolv[2] = {xs[0] ? (double)tol : 1e300, xs[1] ? (double)tol : 1e300};   // the exit test looks at state components
+    // io.phase 2: the "batch" is the list of records parked by the previous launch (count in queue[9], records in park_in);
+    // with io.cap > 0 a resumed instance may be parked again (into io.park).
+    const bool resume = io.phase == 2;
+    const long long B = resume ? min((long long)io.queue[9], io.park_in_cap) : io.B;
+    const WorkQueue wq{resume ? io.queue + 7 : io.queue, B, resume ? nullptr : io.ready};
+    const WorkQueue marks{io.queue, B, nullptr};
+    marks.mark_start();
+    unsigned long long stat_k = 0;
+    unsigned int stat_nc = 0;
+
+    long long inst = -1;
+    int k = 0, grace_left = io.grace;
+    bool live = false, drained = false, park_ok = io.park != nullptr;
+    double y[N][2], lam[N][2], w[N][2], q[2] = {0, 0}, qT[2] = {0, 0};
+    double lo0[2] = {0, 0}, hi0[2] = {0, 0};   // "stage -1": lo = hi = x0 on the state components, the bounds of u_0 on the others
+#pragma unroll
+    for (int l = 0; l < N; ++l)
+#pragma unroll
+        for (int i = 0; i < 2; ++i) y[l][i] = lam[l][i] = w[l][i] = 0.0;
+
+    for (;;) {
+        // ---- refill: a lane group without an instance pulls the next one          code_laxMPC_FISTA_C.c:94-100, 275-289
+        const bool need = !live && !drained;
+        if (__any_sync(FULL, need)) {
+            long long slot = -1;
+            if (need && leader) slot = wq.next();
+            slot = __shfl_sync(FULL, slot, lane & ~3);
+            if (need) {
+                if (slot < 0) {
+                    drained = true;
+                    if (leader) marks.mark_drained();
+                } else {
+                    const double *pk = io.park_in + slot;
+                    inst = resume ? __double_as_longlong(pk[0]) : slot;
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const int e = ec[i];
+                        const double xr_ = xs[i] ? io.xr[inst * n + e] : 0.0;
+                        const double ur_ = us[i] ? io.ur[inst * m + (e - n)] : 0.0;
+                        q[i] = qs[i] * (xs[i] ? xr_ : ur_);          // QRi o [Q xr; R ur]
+                        qT[i] = ts[i] * xr_;                          // Ti o T xr (lax)  |  xr (equ)
+                        if (VARB) {
+                            lb[i] = (e < nm) ? io.LB[inst * nm + e] : -1e300;
+                            ub[i] = (e < nm) ? io.UB[inst * nm + e] : 1e300;
+                        }
+                        double l0, h0;
+                        bnd(0, i, l0, h0);
+                        const double x0_ = xs[i] ? io.x0[inst * n + e] : 0.0;
+                        lo0[i] = xs[i] ? x0_ : l0;
+                        hi0[i] = xs[i] ? x0_ : h0;
+                    }
+                    if (resume) {
+                        k = (int)__double_as_longlong(pk[1 * io.park_in_cap]);
+#pragma unroll
+                        for (int l = 0; l < N; ++l)
+#pragma unroll
+                            for (int i = 0; i < 2; ++i) {
+                                y[l][i] = xs[i] ? pk[(3 + l * n + ec[i]) * io.park_in_cap] : 0.0;
+                                lam[l][i] = xs[i] ? pk[(3 + N * n + l * n + ec[i]) * io.park_in_cap] : 0.0;
+                            }
+                    } else {
+                        k = -1;                                       // the warm-up pass brings it to 0
+#pragma unroll
+                        for (int l = 0; l < N; ++l)
+#pragma unroll
+                            for (int i = 0; i < 2; ++i) y[l][i] = lam[l][i] = 0.0;
+                    }
+                    live = true;
+                }
+            }
+        }
+        if (!__any_sync(FULL, live)) break;
+        const bool dry = (io.phase == 1) && (*(volatile unsigned long long *)io.queue >= (unsigned long long)B);
+
+        // ================= pass A: z(y) -> residual -> exit test -> forward step =================
+        // A warp issues in order, and one DMMA takes 16 issue cycles of the tensor pipe but 26 cycles until its result can be
+        // used: the source order below is the schedule.  Products that do not depend on each other (the same product of
+        // every stage) are issued back to back, k-step 0 of all stages and then k-step 1 of all stages, so the only
+        // latency-exposed MMAs are the two recurrences (mu_l forward, d_lambda_l backward), and the forward one is
+        // interleaved with the independent w_{l-1} = Uinv_{l-1} mu_{l-1} products.
+        // Components that a vector does not use hold finite don't-care values where the consuming matrix has zero columns
+        // (the input part of z_l inside r_l), exact zeros elsewhere; the exit test only looks at state components.
+        double zz[N + 1][2];   // zz[0] = (x0, u_0), zz[l+1] = z_l (l < N-1), zz[N] = z_N (lax) | xr (equ)
+        {
+            // QRi o (q - [A B]' y_s) for every stage s                                      :474-519
+            double e[N][2];
+#pragma unroll
+            for (int s_ = 0; s_ < N; ++s_) dmma(e[s_][0], e[s_][1], y[s_][0], nabt.x, q[0], q[1]);
+#pragma unroll
+            for (int s_ = 0; s_ < N; ++s_) dmma(zz[s_][0], zz[s_][1], y[s_][1], nabt.y, e[s_][0], e[s_][1]);
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i)                                                        // u_0; lo0 = hi0 = x0 on the state part
+            zz[0][i] = clip(PRESCALE ? zz[0][i] : zz[0][i] * qri[i], lo0[i], hi0[i]);
+        const double u0v[2] = {zz[0][0], zz[0][1]};
+#pragma unroll
+        for (int l = 0; l < N - 1; ++l)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                double lo, hi;
+                bnd(l + 1, i, lo, hi);
+                zz[l + 1][i] = clip(PRESCALE ? fma(qri[i], y[l][i], zz[l + 1][i]) : (zz[l + 1][i] + y[l][i]) * qri[i], lo, hi);   // z_l  :494-519
+            }
+#if SPCIES_TERMINAL
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            double lo, hi;
+            bnd(N, i, lo, hi);
+            zz[N][i] = clip(PRESCALE ? fma(ti[i], y[N - 1][i], qT[i]) : (qT[i] + y[N - 1][i]) * ti[i], lo, hi);   // z_N  :522-537
+        }
+#else
+        zz[N][0] = qT[0];                                                                   // xr   code_equMPC_FISTA_C.c:549
+        zz[N][1] = qT[1];
+#endif
+        // r_l = x_{l+1} - [A B] z_{l-1}   (r_0 = x_1 - A x0 - B u_0)                         :549-572
+        double r[N][2];
+        {
+            double e[N][2];
+#pragma unroll
+            for (int l = 0; l < N; ++l) dmma(e[l][0], e[l][1], zz[l][0], nab.x, zz[l + 1][0], zz[l + 1][1]);
+#pragma unroll
+            for (int l = 0; l < N; ++l) dmma(r[l][0], r[l][1], zz[l][1], nab.y, e[l][0], e[l][1]);
+        }
+        bool over = false;
+#pragma unroll
+        for (int l = 0; l < N; ++l) over = over || (fabs(r[l][0]) > tolv[0]) || (fabs(r[l][1]) > tolv[1]);
+        // forward step: mu_l = Linv_l r_l - F_l mu_{l-1};  w_l = Uinv_l mu_l
+        double sl[N][2];
+        {
+            double e[N][2];
+            double2 li[N];
+#pragma unroll
+            for (int l = 0; l < N; ++l) li[l] = mma_mat(T->Linv[l], lane);
+#pragma unroll
+            for (int l = 0; l < N; ++l) dmma(e[l][0], e[l][1], r[l][0], li[l].x, 0.0, 0.0);
+#pragma unroll
+            for (int l = 0; l < N; ++l) dmma(sl[l][0], sl[l][1], r[l][1], li[l].y, e[l][0], e[l][1]);
+        }
+        {
+            double mu[2] = {sl[0][0], sl[0][1]};
+#pragma unroll
+            for (int l = 1; l < N; ++l) {
+                const double2 nf = mma_mat(T->NF[l], lane), ui = mma_mat(T->Uinv[l - 1], lane);
+                double e0, e1, f0, f1, m0, m1;
+                dmma(e0, e1, mu[0], nf.x, sl[l][0], sl[l][1]);       // recurrence, k-step 0
+                dmma(f0, f1, mu[0], ui.x, 0.0, 0.0);                 // w_{l-1}, k-step 0
+                dmma(m0, m1, mu[1], nf.y, e0, e1);                   // recurrence, k-step 1
+                dmma(w[l - 1][0], w[l - 1][1], mu[1], ui.y, f0, f1); // w_{l-1}, k-step 1
+                mu[0] = m0;
+                mu[1] = m1;
+            }
+            mma_mv(w[N - 1], mma_mat(T->Uinv[N - 1], lane), mu, 0.0, 0.0);
+        }
+
+        // ================= exit condition                                            :337-361 =================
+        if (live) k += 1;
+        const bool gover = (__ballot_sync(FULL, over) & gmask) != 0u;
+        if (live && k >= 1) {
+            int ef = 0;
+            if (!gover) ef = 1;
+            else if (k >= k_max) ef = -1;
+            if (ef != 0) {
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+                    if (us[i]) io.u[inst * m + (ec[i] - n)] = u0v[i];
+                if (leader) {
+                    io.k[inst] = k;
+                    io.e[inst] = ef;
+                    stat_k += (unsigned long long)k;
+                    stat_nc += (ef < 0);
+                }
+                live = false;
+            }
+        }
+
+        // ================= pass B: backward step, lambda and y updates      :368-385, :619-648 =================
+        const double beta = T->beta[(live && k > 0) ? k : 0];
+        double d[2] = {w[N - 1][0], w[N - 1][1]};
+#pragma unroll
+        for (int l = N - 1; l >= 0; --l) {
+            if (l < N - 1) {
+                mma_mv(d, mma_mat(T->NG[l], lane), d, w[l][0], w[l][1]);   // d_lambda_l = w_l - G_l d_lambda_{l+1}
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const double ln = y[l][i] + d[i];                   // lambda_l = y_l + d_lambda_l
+                y[l][i] = fma(beta, ln - lam[l][i], ln);            // y_l = lambda_l + beta (lambda_l - lambda1_l)
+                lam[l][i] = ln;
+            }
+        }
+
+        // ---- parking: an instance that is still running `grace` iterations after the queue ran dry (io.phase 1), or that
+        //      has reached the iteration cap of this launch (io.cap), hands its iterates to the next launch
+        bool park_now = false;
+        if (dry && live && k >= 1) {
+            park_now = grace_left <= 0;
+            grace_left -= 1;
+        }
+        if (io.cap > 0 && live && k >= io.cap) park_now = true;
+        park_now = park_now && park_ok;
+        if (__any_sync(FULL, park_now)) {
+            long long pslot = 0;
+            if (park_now && leader) pslot = (long long)atomicAdd(io.queue + 6, 1ULL);
+            pslot = __shfl_sync(FULL, pslot, lane & ~3);
+            if (park_now && pslot >= io.park_cap) {                 // no room: the instance stays where it is
+                park_now = false;
+                park_ok = false;
+            }
+            if (park_now) {
+                double *pk = io.park + pslot;
+                if (leader) {
+                    atomicAdd(io.queue + 10, 1ULL);
+                    pk[0] = __longlong_as_double(inst);
+                    pk[1 * io.park_cap] = __longlong_as_double((long long)k);
+                    pk[2 * io.park_cap] = 0.0;                      // t: implied by k in this engine
+                }
+#pragma unroll
+                for (int l = 0; l < N; ++l)
+#pragma unroll
+                    for (int i = 0; i < 2; ++i)
+                        if (xs[i]) {
+                            pk[(3 + l * n + ec[i]) * io.park_cap] = y[l][i];
+                            pk[(3 + N * n + l * n + ec[i]) * io.park_cap] = lam[l][i];
+                        }
+                live = false;
+            }
+        }
+    }
+    flush_stats(io.queue, stat_k, stat_nc);
+    marks.mark_end();
+}

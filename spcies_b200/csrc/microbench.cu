@@ -92,6 +92,25 @@ __global__ void smem_stream(double *out, int iters) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = s0 + s1 + s2 + s3;
 }
 
+// FP64 tensor-core issue rate: m8n8k4 MMA (SASS DMMA.8x8x4, 256 FMA per warp instruction), 4 independent accumulators
+__global__ void dmma_regs(double *out, int iters) {
+    double a = 1e-3 * threadIdx.x, b = 2e-3 * threadIdx.x, d[4][2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) d[j][0] = d[j][1] = j;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                             : "+d"(d[j][0]), "+d"(d[j][1]) : "d"(a), "d"(b));
+    }
+    double s = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s += d[j][0] + d[j][1];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 template <class F> static double time_ms(F launch, int reps = 5) {
     cudaEvent_t a, b;
     CK(cudaEventCreate(&a));
@@ -159,6 +178,11 @@ int main(int argc, char **argv) {
         printf(", \"fp64_tfma_per_s_cbank6KB_%dwarps\": %.3f", warps, run_cbank<768>(d_out, sms, block, iters));
         printf(", \"fp64_tfma_per_s_cbank13KB_%dwarps\": %.3f", warps, run_cbank<1664>(d_out, sms, block, iters));
         printf(", \"fp64_tfma_per_s_cbank40KB_%dwarps\": %.3f", warps, run_cbank<5120>(d_out, sms, block, iters / 2));
+    }
+    {   // DMMA: the ceiling of the tensor-core engine (MPC_FISTA_mma.cuh); shares the FP64 datapath with DFMA
+        const int block = 256, iters = 2000;
+        double ms = time_ms([&] { dmma_regs<<<sms, block>>>(d_out, iters); });
+        printf(", \"fp64_dmma_tfma_per_s\": %.3f", (double)sms * (block / 32) * iters * 32.0 * 256.0 / (ms * 1e-3) / 1e12);
     }
     {   // shared-memory streaming in the iterate layout: 128 threads x 200 doubles (the FISTA N=10 footprint)
         const int block = 128, elems = 200, iters = 2000;

@@ -137,6 +137,7 @@ struct BatchIO {
                                       // [3] ~(first time a lane found the queue empty), [4] ~(kernel start), [5] kernel end
                                       //     (globaltimer ns; min kept as max of the complement so that memset(0) initialises)
                                       // [6] number of parked instances, [7] next parked record (phase 2)
+                                      // [9] number of records to resume (copy of [6] made between two launches), [10] park events
     // tail handling of kernels that support it (Traits::HAS_PARK): see MPC_FISTA.cuh
     double *park;                     // [PARK_DOUBLES][park_cap] records of parked instances, element-major
     long long park_cap;
@@ -144,6 +145,10 @@ struct BatchIO {
                                       // 1: park the instances still running `grace` iterations after the queue ran dry
                                       // 2: resume the parked instances (B is read from queue[6])
     int grace;
+    const double *park_in;            // phase 2 of kernels with iteration caps: the records to resume (count in queue[9]) ...
+    long long park_in_cap;            // ... while `park` receives the instances that reach this launch's cap
+    int cap;                          // > 0: park an instance once it has done `cap` iterations (MPC_FISTA_mma.cuh)
+    int engine;                       // spcies_batch_opts.engine (kernels with more than one engine, MPC_FISTA.cuh)
     const unsigned long long *ready;  // optional: instances [0, *ready) have their inputs in device memory (the host->device
                                       // copies of a host-buffer call run on a second stream, chunk by chunk, under the kernel)
 };

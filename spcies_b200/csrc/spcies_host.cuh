@@ -64,6 +64,7 @@ struct DeviceCtx {
     void *d_scratch = nullptr;   // per-instance state of solvers whose iterates do not fit shared memory
     size_t cap_scratch = 0;
     double *d_park = nullptr;    // parked-instance records (tail handling, Traits::HAS_PARK)
+    double *d_park2 = nullptr;   // second record buffer of the iteration-cap rounds (a round resumes from one, parks into the other)
     long long cap_park = 0;
 };
 
@@ -154,7 +155,7 @@ template <class Traits> struct Runtime {
             cudaSetDevice(c.dev);
             cudaFree(c.d_consts); cudaFree(c.d_queue);
             cudaFree(c.d_x0); cudaFree(c.d_xr); cudaFree(c.d_ur); cudaFree(c.d_r); cudaFree(c.d_LB); cudaFree(c.d_UB);
-            cudaFree(c.d_u); cudaFree(c.d_sol); cudaFree(c.d_k); cudaFree(c.d_e); cudaFree(c.d_scratch); cudaFree(c.d_park);
+            cudaFree(c.d_u); cudaFree(c.d_sol); cudaFree(c.d_k); cudaFree(c.d_e); cudaFree(c.d_scratch); cudaFree(c.d_park); cudaFree(c.d_park2);
             for (auto &e : c.ev) cudaEventDestroy(e);
             cudaStreamDestroy(c.stream);
             cudaStreamDestroy(c.copy_stream);
@@ -170,7 +171,8 @@ template <class Traits> struct Runtime {
         int *k, *e;
         double *sol;
         int arith, block, grid;
-        int tail_mode, tail_grace;
+        int tail_mode, tail_grace, engine;
+        int tail_caps[3];
         bool device_pointers;
         cudaStream_t user_stream;
     };
@@ -207,9 +209,12 @@ template <class Traits> struct Runtime {
             io.LB = varb ? c.d_LB : nullptr; io.UB = varb ? c.d_UB : nullptr;
             io.u = c.d_u; io.k = c.d_k; io.e = c.d_e; io.sol = cl.sol ? c.d_sol : nullptr;
         }
+        io.engine = cl.engine;
         int block = cl.block > 0 ? cl.block : Traits::default_block(varb);
         size_t smem = Traits::smem_bytes(block, varb);
-        long long want = (B + block - 1) / block;
+        int ipb = block;                                 // instances resident per CTA
+        Traits::engine_shape(cl.arith, io, block, smem, ipb);
+        long long want = (B + ipb - 1) / ipb;
         int grid = cl.grid > 0 ? cl.grid : c.sm_count;   // persistent: one CTA per SM
         if (want < grid) grid = (int)(want > 0 ? want : 1);
         const size_t need_scratch = Traits::scratch_bytes(grid, block, varb);
@@ -219,19 +224,39 @@ template <class Traits> struct Runtime {
             SPCIES_CK(cudaMalloc(&c.d_scratch, need_scratch));
             c.cap_scratch = need_scratch;
         }
-        // tail handling: two launches (park & resume) when the kernel supports it and the batch is larger than one wave
+        // tail handling (kernels that can park & resume instances, Traits::HAS_PARK), batches larger than four waves:
+        //   two_phase  park the instances still running shortly after the queue ran dry, resume them in a second launch
+        //   caps       iteration-cap rounds (engines with Traits::caps_engine): launch r runs every instance it holds up to
+        //              caps[r] iterations and parks the rest, so that the slow instances are all known -- and all start -- early
+        //              instead of trailing the launch one by one; the last round has no cap
         bool two_phase = false;
+        int caps[4] = {0, 0, 0, 0}, ncaps = 0;
         if constexpr (Traits::HAS_PARK) {
-            two_phase = cl.tail_mode == SPCIES_CUDA_TAIL_TWO_PHASE ||
-                        (cl.tail_mode == SPCIES_CUDA_TAIL_AUTO && B > 4LL * grid * block);
-            if (two_phase) {
-                const long long need = (long long)grid * block;
+            const bool big = B > 4LL * grid * ipb;
+            const bool caps_ok = Traits::caps_engine(cl.arith, io);
+            int mode = cl.tail_mode;
+            if (mode == SPCIES_CUDA_TAIL_AUTO) mode = !big ? SPCIES_CUDA_TAIL_SINGLE : (caps_ok ? SPCIES_CUDA_TAIL_CAPS : SPCIES_CUDA_TAIL_TWO_PHASE);
+            if (mode == SPCIES_CUDA_TAIL_CAPS && !caps_ok) mode = SPCIES_CUDA_TAIL_TWO_PHASE;
+            two_phase = mode == SPCIES_CUDA_TAIL_TWO_PHASE;
+            if (mode == SPCIES_CUDA_TAIL_CAPS) {
+                const int dflt[3] = {96, 320, 0};
+                const int *want_caps = cl.tail_caps[0] > 0 ? cl.tail_caps : dflt;
+                for (int i = 0; i < 3 && want_caps[i] > 0; ++i)
+                    if (want_caps[i] < Traits::K_MAX && (ncaps == 0 || want_caps[i] > caps[ncaps - 1])) caps[ncaps++] = want_caps[i];
+            }
+            if (two_phase || ncaps > 0) {
+                long long need = (long long)grid * block;
+                if (ncaps > 0) need = std::max<long long>(4LL * grid * ipb, B / 16 + 1024);
                 if (need > c.cap_park) {
                     if (c.d_park) SPCIES_CK(cudaFree(c.d_park));
-                    c.d_park = nullptr;
+                    if (c.d_park2) SPCIES_CK(cudaFree(c.d_park2));
+                    c.d_park = c.d_park2 = nullptr;
+                    c.cap_park = 0;
                     SPCIES_CK(cudaMalloc((void **)&c.d_park, (size_t)need * Traits::PARK_DOUBLES * sizeof(double)));
                     c.cap_park = need;
                 }
+                if (ncaps > 1 && !c.d_park2)
+                    SPCIES_CK(cudaMalloc((void **)&c.d_park2, (size_t)c.cap_park * Traits::PARK_DOUBLES * sizeof(double)));
                 io.park = c.d_park;
                 io.park_cap = c.cap_park;
                 io.grace = cl.tail_grace > 0 ? cl.tail_grace : 32;
@@ -276,16 +301,28 @@ template <class Traits> struct Runtime {
         }
         SPCIES_CK(cudaEventRecord(c.ev[1], s));
         if (B > 0) {
-            io.phase = two_phase ? 1 : 0;
+            io.phase = (two_phase || ncaps > 0) ? 1 : 0;
+            io.grace = two_phase ? io.grace : (1 << 30);
+            io.cap = ncaps > 0 ? caps[0] : 0;
             SPCIES_CK(Traits::launch(cl.arith, varb, grid, block, smem, s, io, c.d_consts, c.d_scratch));
             res.launches = 1;
             if constexpr (Traits::HAS_PARK) {
-                if (two_phase) {
+                const int rounds = two_phase ? 1 : ncaps;          // resume launches
+                for (int r = 0; r < rounds; ++r) {
+                    // the records parked by the previous launch become this launch's queue
+                    SPCIES_CK(cudaMemcpyAsync(c.d_queue + 9, c.d_queue + 6, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, s));
+                    if (ncaps > 0) SPCIES_CK(cudaMemsetAsync(c.d_queue + 6, 0, 2 * sizeof(unsigned long long), s));
                     io.phase = 2;
-                    const int block2 = Traits::resume_block(varb);
-                    SPCIES_CK(Traits::launch(cl.arith, varb, c.sm_count, block2, Traits::smem_bytes(block2, varb), s, io, c.d_consts,
-                                             c.d_scratch));
-                    res.launches = 2;
+                    io.park_in = (r % 2 == 0) ? c.d_park : c.d_park2;
+                    io.park_in_cap = c.cap_park;
+                    io.park = (r + 1 < rounds) ? ((r % 2 == 0) ? c.d_park2 : c.d_park) : (two_phase ? c.d_park : nullptr);
+                    io.cap = (r + 1 < rounds) ? caps[r + 1] : 0;
+                    io.ready = nullptr;
+                    int block2 = Traits::resume_block(varb), ipb2 = 0;
+                    size_t smem2 = Traits::smem_bytes(block2, varb);
+                    Traits::engine_shape(cl.arith, io, block2, smem2, ipb2);
+                    SPCIES_CK(Traits::launch(cl.arith, varb, c.sm_count, block2, smem2, s, io, c.d_consts, c.d_scratch));
+                    res.launches += 1;
                 }
             }
         }
@@ -314,7 +351,7 @@ template <class Traits> struct Runtime {
         }
         res.sum_k = (long long)stats[1];
         res.n_nc = (long long)stats[2];
-        res.parked = (long long)stats[6];
+        res.parked = ncaps > 0 ? (long long)stats[10] : (long long)stats[6];
         if (stats[4] && stats[5]) {
             const unsigned long long t_start = ~stats[4], t_drain = stats[3] ? ~stats[3] : stats[5];
             res.span_us = (int)((stats[5] - t_start) / 1000ULL);
@@ -358,7 +395,8 @@ template <class Traits> struct Runtime {
             c.u = u + lo * Traits::MM; c.k = k + lo; c.e = e + lo;
             c.sol = sol ? sol + lo * (long long)Traits::SOL_DOUBLES : nullptr;
             c.arith = o.arith; c.block = o.block_threads; c.grid = o.grid_blocks;
-            c.tail_mode = o.tail_mode; c.tail_grace = o.tail_grace;
+            c.tail_mode = o.tail_mode; c.tail_grace = o.tail_grace; c.engine = o.engine;
+            for (int i = 0; i < 3; ++i) c.tail_caps[i] = o.tail_caps[i];
             c.device_pointers = o.device_pointers != 0;
             c.user_stream = (cudaStream_t)o.stream;
         }

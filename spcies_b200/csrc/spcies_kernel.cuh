@@ -121,6 +121,9 @@ template <class S> struct PolicyTraits {
     static size_t blob_bytes() { return sizeof(spcies_consts); }
     static void fill_blob(void *dst) { memcpy(dst, &spcies_h_consts, sizeof spcies_h_consts); }
     static int resume_block(bool varb) { return default_block(varb); }
+    static void engine_shape(int, const BatchIO &, int &block, size_t &, int &ipb) { ipb = block; }
+    static bool caps_engine(int, const BatchIO &) { return false; }
+    static constexpr int K_MAX = 0;
     static cudaError_t init_device_symbols() { return cudaSuccess; }
     static int default_block(bool varb) { return varb ? P::BLOCK_VARB : P::BLOCK_FIXED; }
     static bool gstate(bool varb) { return varb ? P::GSTATE_VARB : P::GSTATE_FIXED; }

@@ -21,7 +21,7 @@ class BatchOpts(ctypes.Structure):
     _fields_ = [('device', c_int), ('n_devices', c_int), ('arith', c_int), ('device_pointers', c_int),
                 ('LB', c_void_p), ('UB', c_void_p), ('stream', c_void_p),
                 ('block_threads', c_int), ('grid_blocks', c_int), ('tail_mode', c_int), ('tail_grace', c_int),
-                ('reserved', c_int * 6)]
+                ('engine', c_int), ('tail_caps', c_int * 3), ('reserved', c_int * 2)]
 
 
 class BatchInfo(ctypes.Structure):
@@ -36,7 +36,8 @@ class BatchInfo(ctypes.Structure):
 
 
 ARITH_FAST, ARITH_EXACT = 0, 1
-TAIL_AUTO, TAIL_SINGLE, TAIL_TWO_PHASE = 0, 1, 2
+TAIL_AUTO, TAIL_SINGLE, TAIL_TWO_PHASE, TAIL_CAPS = 0, 1, 2, 3
+ENGINE_AUTO, ENGINE_SCALAR, ENGINE_MMA = 0, 1, 2
 
 
 class SpciesCudaError(RuntimeError):
@@ -129,7 +130,7 @@ class CudaSolver:
         return u, k.value, e.value, self._split_sol(sol)
 
     def solve_batch(self, x0, xr, ur, r=None, LB=None, UB=None, arith=ARITH_FAST, device=0, n_devices=1,
-                    want_sol=False, out=None, block_threads=0, grid_blocks=0, tail_mode=0, tail_grace=0):
+                    want_sol=False, out=None, block_threads=0, grid_blocks=0, tail_mode=0, tail_grace=0, engine=0, tail_caps=()):
         """B instances through ``<func>_batch``.  Arrays are ``[B, n]`` / ``[B, m]`` (instance-major)."""
         x0 = np.ascontiguousarray(x0, dtype=np.float64)
         xr = np.ascontiguousarray(xr, dtype=np.float64)
@@ -148,6 +149,9 @@ class CudaSolver:
         opts.device, opts.n_devices, opts.arith = int(device), int(n_devices), int(arith)
         opts.block_threads, opts.grid_blocks = int(block_threads), int(grid_blocks)
         opts.tail_mode, opts.tail_grace = int(tail_mode), int(tail_grace)
+        opts.engine = int(engine)
+        for i, c in enumerate(tuple(tail_caps)[:3]):
+            opts.tail_caps[i] = int(c)
         keep = []
         if LB is not None or UB is not None:
             LB = np.ascontiguousarray(LB, dtype=np.float64)
@@ -171,12 +175,15 @@ class CudaSolver:
         return u, k, e, info.as_dict()
 
     def solve_batch_device(self, B, d_x0, d_xr, d_ur, d_u, d_k, d_e, d_r=None, d_LB=None, d_UB=None, arith=ARITH_FAST,
-                           device=0, stream=None, block_threads=0, grid_blocks=0, tail_mode=0, tail_grace=0):
+                           device=0, stream=None, block_threads=0, grid_blocks=0, tail_mode=0, tail_grace=0, engine=0, tail_caps=()):
         """Same call with DEVICE pointers (integers), e.g. ``tensor.data_ptr()``: no copies, kernel only."""
         opts = BatchOpts()
         opts.device, opts.n_devices, opts.arith, opts.device_pointers = int(device), 1, int(arith), 1
         opts.block_threads, opts.grid_blocks = int(block_threads), int(grid_blocks)
         opts.tail_mode, opts.tail_grace = int(tail_mode), int(tail_grace)
+        opts.engine = int(engine)
+        for i, c in enumerate(tuple(tail_caps)[:3]):
+            opts.tail_caps[i] = int(c)
         opts.LB = d_LB
         opts.UB = d_UB
         opts.stream = stream

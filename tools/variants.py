@@ -16,8 +16,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 VARIANTS = {
-    'smem4w': ['-DSPCIES_FISTA_TMEM=0'],
-    'tmem8w': ['-DSPCIES_FISTA_TMEM=1'],
+    'scalar_tmem8w': ['-DSPCIES_FISTA_MMA=0'],
+    'mma256': [],
+    'mma384': ['-DSPCIES_FISTA_MMA_BLOCK=384'],
 }
 VARIANTS.update(json.loads(os.environ.get('SPCIES_VARIANTS', '{}')))
 LIST = os.path.join(ROOT, 'generated_solvers', 'variants.json')
@@ -33,8 +34,8 @@ def build():
         cu, _ = cuda_code.emit(spec, save_name=save)
         so = cuda_code.build(cu, extra_flags=tuple(flags))
         log = open(cu[:-3] + '.stamp').read()
-        regs = [l.strip() for l in log.split('\n') if 'Used' in l]
-        print(save, flags, regs[:1])
+        regs = [l.strip() for l in log.split('\n') if 'Used' in l or 'spill' in l]
+        print(save, flags, regs[-2:])
         done[name] = flags
     json.dump(done, open(LIST, 'w'))
 
@@ -73,15 +74,19 @@ def run(B):
                     two_phase_same_bits=bool(np.array_equal(u.view(np.uint64), u1.view(np.uint64)) and np.array_equal(k, k1)),
                     parked=info['parked'])
         out[name] = dict(exact=exact, exact_two_phase=exact2, parked_small=parked_small, fast=fast, runs={})
-        for mode, grace in ((1, 0), (0, 32), (0, 16), (0, 64), (0, 128)):
+        runs = [(1, 0, ()), (2, 32, ()), (3, 0, (96, 320)), (3, 0, (64,)), (3, 0, (128,)), (3, 0, (64, 256)), (3, 0, (48, 160, 480)),
+                (3, 0, (128, 400))]
+        if 'scalar' in name:
+            runs = [(1, 0, ()), (2, 32, ())]
+        for mode, grace, caps in runs:
             ms = []
             for i in range(4):
                 info = sol.solve_batch_device(B, d['x0'].data_ptr(), d['xr'].data_ptr(), d['ur'].data_ptr(), d_u.data_ptr(),
-                                              d_k.data_ptr(), d_e.data_ptr(), tail_mode=mode, tail_grace=grace)
+                                              d_k.data_ptr(), d_e.data_ptr(), tail_mode=mode, tail_grace=grace, tail_caps=caps)
                 ms.append(info['kernel_ms'])
-            out[name]['runs'][f'mode{mode}_g{grace}'] = dict(kernel_ms=min(ms[1:]), drain_us=info['drain_us'], span_us=info['span_us'],
-                                                             parked=info['parked'], launches=info['launches'],
-                                                             Msolves_s=B / min(ms[1:]) / 1e3)
+            out[name]['runs'][f'mode{mode}_g{grace}_c{"-".join(map(str, caps))}'] = dict(
+                kernel_ms=min(ms[1:]), drain_us=info['drain_us'], span_us=info['span_us'], parked=info['parked'],
+                launches=info['launches'], Msolves_s=B / min(ms[1:]) / 1e3)
         out[name].update(block=info['block_threads'], regs=info['regs_per_thread'], smem=info['smem_bytes'], sum_k=info['sum_k'])
         print(name, json.dumps(out[name]), flush=True)
         sol.free()

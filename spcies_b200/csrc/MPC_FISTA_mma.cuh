@@ -35,6 +35,9 @@
 #define SPCIES_FISTA_MMA_PRESCALE 1  // 1: fold the QRi / Ti scalings of z into [A B]' and q (one FP64 operation less per component of z;
                                      // the constants are rounded once more: same measured accuracy, tools/diag_equ.py)
 #endif
+#ifndef SPCIES_FISTA_MMA_MERGE
+#define SPCIES_FISTA_MMA_MERGE 1     // 1: permuted component layout that lets two n-vector products share a k-step (5 <= nn_ <= 6)
+#endif
 #ifndef SPCIES_FISTA_MMA_BLOCK
 #define SPCIES_FISTA_MMA_BLOCK 256
 #endif
@@ -45,14 +48,55 @@ constexpr bool HAS_MMA = SPCIES_FISTA_MMA != 0 && sizeof(real) == 8 && nm <= 8 &
 constexpr int MMA_KTAB = k_max + 2;
 constexpr bool PRESCALE = SPCIES_FISTA_MMA_PRESCALE != 0;
 
+// Component layout.  A vector of an instance is 8 "columns" (column c lives in lane t = c / 2 of the group, register c % 2).
+// An MMA k-step consumes one register of the 4 lanes, i.e. columns {0,2,4,6} or {1,3,5,7}.
+//   plain   column = component: x_e -> e, u_j -> n + j.  Every product with an n-vector (n = 6) wastes a quarter of both k-steps.
+//   MERGE   x_0..x_3 -> 0,2,4,6 (a full k-step), x_4.. -> 1,3 (half a k-step), u_j -> the columns after them (5,7).  The
+//           vectors of the two recurrences (mu, d_lambda) carry a second copy of x_4.. in columns 5,7 -- free, the matrix
+//           rows are duplicated -- so the half k-steps of two products that add up (Linv_l r_l + (-F_l) mu_{l-1}, and
+//           Uinv_l mu_l + (-G_l) d_lambda_{l+1}) merge into one:  a = lane < 2 ? r.reg1 : mu.reg1.  3 MMAs instead of 4, twice
+//           per stage: 98 instead of 116 DMMA per iteration at N = 10.
+constexpr bool MERGE = SPCIES_FISTA_MMA_MERGE != 0 && PRESCALE && n >= 5 && n <= 6 && nm <= 8;
+__host__ __device__ constexpr int col_x(int e) { return MERGE ? (e < 4 ? 2 * e : 2 * (e - 4) + 1) : e; }
+__host__ __device__ constexpr int col_u(int j) { return MERGE ? 2 * (n - 4 + j) + 1 : n + j; }
+__host__ __device__ constexpr int col_dup(int e) { return 2 * (e - 4 + 2) + 1; }   // MERGE: second copy of x_e, e >= 4
+__host__ __device__ constexpr int x_at(int c) {
+    for (int e = 0; e < n; ++e)
+        if (col_x(e) == c) return e;
+    return -1;
+}
+__host__ __device__ constexpr int u_at(int c) {
+    for (int j = 0; j < m; ++j)
+        if (col_u(j) == c) return j;
+    return -1;
+}
+__host__ __device__ constexpr int z_at(int c) { return x_at(c) >= 0 ? x_at(c) : (u_at(c) >= 0 ? n + u_at(c) : -1); }   // component of z = (x, u)
+// component of mu / d_lambda produced in output column c (MERGE: including the second copies)
+__host__ __device__ constexpr int xo_at(int c) {
+    if (x_at(c) >= 0) return x_at(c);
+    if (MERGE)
+        for (int e = 4; e < n; ++e)
+            if (col_dup(e) == c) return e;
+    return -1;
+}
+
 struct alignas(16) MmaTables {
-    double SNABt[64];         // -[A B]'  (out nm, in n)   [PRESCALE: -diag(QRi) [A B]', the scaling of z folded into the product]
-    double NAB[64];           // -[A B]   (out n, in nm)
-    double Linv[N][64], NF[N][64], Uinv[N][64], NG[N][64];
-    double QRi[8], Ti[8];     // component scalings (stored negated by the generator, like Q, R, T)
+    // every table is indexed by column (see the layout above); matrices are row-major [output column][input column]
+    double SNABt[64];         // -[A B]'  (out z, in x)   [PRESCALE: -diag(QRi) [A B]', the scaling of z folded into the product]
+    double NAB[64];           // -[A B]   (out x, in z)
+    // plain layout: one 8 x 8 matrix per product and stage
+    double Linv[MERGE ? 1 : N][64], NF[MERGE ? 1 : N][64], Uinv[MERGE ? 1 : N][64], NG[MERGE ? 1 : N][64];
+    // MERGE layout, per stage and lane (o = lane / 4 output column, t = lane % 4):
+    //   FWa = (Linv[o][x_t], -F[o][x_t]),  FWb = t < 2 ? Linv[o][x_{4+t}] : -F[o][x_{4+t-2}]      (F = 0 at stage 0)
+    //   BWa = (Uinv[o][x_t], -G[o][x_t]),  BWb = t < 2 ? Uinv[o][x_{4+t}] : -G[o][x_{4+t-2}]      (G = 0 at stage N-1)
+    double2 FWa[MERGE ? N : 1][32], BWa[MERGE ? N : 1][32];
+    double FWb[MERGE ? N : 1][32], BWb[MERGE ? N : 1][32];
+    double QRiz[8], QRiy[8];  // scaling of z by column: all of z  |  state columns only (multiplies y_l)
+    double Ti[8];             // component scalings are stored negated by the generator, like Q, R, T
     double Qs[8], Ts[8];      // q = Qs o [xr; ur],  qT = Ts o xr (lax) | xr (equ)   [PRESCALE: times QRi, Ti]
-    double LBs[N + 1][8];     // row 0: u_0 (components n..nm-1), rows 1..N-1: stage l = row - 1, row N: terminal state
+    double LBs[N + 1][8];     // row 0: u_0, rows 1..N-1: stage l = row - 1, row N: terminal state; -1e300 / 1e300 where unused
     double UBs[N + 1][8];
+    int xat[8], uat[8];       // component of x / u held by a column, or -1
     double beta[MMA_KTAB];    // momentum coefficient of the pass that follows the k-th exit test (0 for k = 0, 1)
 };
 constexpr size_t MMA_BYTES = (sizeof(MmaTables) + 15) / 16 * 16;
@@ -61,58 +105,85 @@ constexpr size_t TOTAL_BLOB_BYTES = BLOB_BYTES + MMA_BYTES;
 
 static inline void fill_mma_tables(const spcies_consts &C, const FistaDerived &D, MmaTables &T) {
     memset(&T, 0, sizeof T);
-    for (int i = 0; i < n; ++i)
-        for (int j = 0; j < nm; ++j) {
-            T.SNABt[j * 8 + i] = PRESCALE ? -(double)C.QRi[j] * (double)C.AB[i][j] : -(double)C.AB[i][j];
-            T.NAB[i * 8 + j] = -(double)C.AB[i][j];
+    for (int c = 0; c < 8; ++c) {
+        T.xat[c] = x_at(c);
+        T.uat[c] = u_at(c);
+    }
+    for (int oc = 0; oc < 8; ++oc)
+        for (int ic = 0; ic < 8; ++ic) {
+            if (z_at(oc) >= 0 && x_at(ic) >= 0)
+                T.SNABt[oc * 8 + ic] = -(PRESCALE ? (double)C.QRi[z_at(oc)] : 1.0) * (double)C.AB[x_at(ic)][z_at(oc)];
+            if (x_at(oc) >= 0 && z_at(ic) >= 0) T.NAB[oc * 8 + ic] = -(double)C.AB[x_at(oc)][z_at(ic)];
         }
-    for (int l = 0; l < N; ++l)
-        for (int i = 0; i < n; ++i)
-            for (int j = 0; j < n; ++j) {
-                T.Linv[l][i * 8 + j] = (double)D.Linv[l][i][j];
-                T.NF[l][i * 8 + j] = -(double)D.F[l][i][j];
-                T.Uinv[l][i * 8 + j] = (double)D.Uinv[l][i][j];
-                T.NG[l][i * 8 + j] = -(double)D.G[l][i][j];
+    for (int l = 0; l < N; ++l) {
+        if constexpr (!MERGE) {
+            for (int i = 0; i < n; ++i)
+                for (int j = 0; j < n; ++j) {
+                    T.Linv[l][i * 8 + j] = (double)D.Linv[l][i][j];
+                    T.NF[l][i * 8 + j] = -(double)D.F[l][i][j];
+                    T.Uinv[l][i * 8 + j] = (double)D.Uinv[l][i][j];
+                    T.NG[l][i * 8 + j] = -(double)D.G[l][i][j];
+                }
+        } else {
+            for (int lane = 0; lane < 32; ++lane) {
+                const int o = xo_at(lane / 4), t = lane % 4;
+                if (o < 0) continue;
+                const int e0 = x_at(2 * t);                      // component in the full k-step (columns 0,2,4,6)
+                const int e1 = 4 + (t < 2 ? t : t - 2);          // component in the shared k-step
+                if (e0 >= 0) {
+                    T.FWa[l][lane] = make_double2((double)D.Linv[l][o][e0], -(double)D.F[l][o][e0]);
+                    T.BWa[l][lane] = make_double2((double)D.Uinv[l][o][e0], -(double)D.G[l][o][e0]);
+                }
+                if (e1 < n) {
+                    T.FWb[l][lane] = t < 2 ? (double)D.Linv[l][o][e1] : -(double)D.F[l][o][e1];
+                    T.BWb[l][lane] = t < 2 ? (double)D.Uinv[l][o][e1] : -(double)D.G[l][o][e1];
+                }
             }
-    for (int e = 0; e < nm; ++e) T.QRi[e] = (double)C.QRi[e];
-    for (int e = 0; e < n; ++e) {
-        T.Qs[e] = PRESCALE ? (double)C.QRi[e] * (double)C.Q[e] : (double)C.Q[e];
-#if SPCIES_TERMINAL
-        T.Ti[e] = (double)C.Ti[e];
-        T.Ts[e] = PRESCALE ? (double)C.Ti[e] * (double)C.T[e] : (double)C.T[e];
-#else
-        T.Ts[e] = 1.0;
-#endif
-    }
-    for (int j = 0; j < m; ++j) T.Qs[n + j] = PRESCALE ? (double)C.QRi[n + j] * (double)C.R[j] : (double)C.R[j];
-    for (int s = 0; s <= N; ++s)
-        for (int e = 0; e < 8; ++e) {
-            T.LBs[s][e] = -1e300;
-            T.UBs[s][e] = 1e300;
         }
+    }
+    for (int s = 0; s <= N; ++s)
+        for (int c = 0; c < 8; ++c) {
+            T.LBs[s][c] = -1e300;
+            T.UBs[s][c] = 1e300;
+        }
+    for (int c = 0; c < 8; ++c) {
+        const int e = x_at(c), j = u_at(c), z = z_at(c);
+        if (z >= 0) T.QRiz[c] = (double)C.QRi[z];
+        if (e >= 0) {
+            T.QRiy[c] = (double)C.QRi[e];
+            T.Qs[c] = (PRESCALE ? (double)C.QRi[e] : 1.0) * (double)C.Q[e];
+#if SPCIES_TERMINAL
+            T.Ti[c] = (double)C.Ti[e];
+            T.Ts[c] = (PRESCALE ? (double)C.Ti[e] : 1.0) * (double)C.T[e];
+#else
+            T.Ts[c] = 1.0;
+#endif
+        }
+        if (j >= 0) T.Qs[c] = (PRESCALE ? (double)C.QRi[n + j] : 1.0) * (double)C.R[j];
 #ifdef VAR_BOUNDS
-    for (int j = 0; j < m; ++j) {
-        T.LBs[0][n + j] = (double)C.LB0[j];
-        T.UBs[0][n + j] = (double)C.UB0[j];
-    }
-    for (int l = 0; l < N - 1; ++l)
-        for (int e = 0; e < nm; ++e) {
-            T.LBs[l + 1][e] = (double)C.LB[l][e];
-            T.UBs[l + 1][e] = (double)C.UB[l][e];
+        if (j >= 0) {
+            T.LBs[0][c] = (double)C.LB0[j];
+            T.UBs[0][c] = (double)C.UB0[j];
         }
+        if (z >= 0)
+            for (int l = 0; l < N - 1; ++l) {
+                T.LBs[l + 1][c] = (double)C.LB[l][z];
+                T.UBs[l + 1][c] = (double)C.UB[l][z];
+            }
 #if SPCIES_TERMINAL
-    for (int e = 0; e < n; ++e) {
-        T.LBs[N][e] = (double)C.LBN[e];
-        T.UBs[N][e] = (double)C.UBN[e];
-    }
+        if (e >= 0) {
+            T.LBs[N][c] = (double)C.LBN[e];
+            T.UBs[N][c] = (double)C.UBN[e];
+        }
 #endif
 #else
-    for (int s = 0; s <= N; ++s)
-        for (int e = 0; e < nm; ++e) {
-            T.LBs[s][e] = (double)C.LB[e];
-            T.UBs[s][e] = (double)C.UB[e];
-        }
+        if (z >= 0)
+            for (int s = 0; s <= N; ++s) {
+                T.LBs[s][c] = (double)C.LB[z];
+                T.UBs[s][c] = (double)C.UB[z];
+            }
 #endif
+    }
     // t_0 = 1;  t_k = (1 + sqrt(1 + 4 t_{k-1}^2)) / 2;  beta_k = (t_{k-1} - 1) / t_k      code_laxMPC_FISTA_C.c:370-385
     volatile double t = 1.0;
     T.beta[0] = 0.0;
@@ -149,34 +220,38 @@ __global__ void __launch_bounds__(MMA_BLOCK, 1) fista_mma_kernel(const BatchIO i
     stage_constants(smem_raw, g_blob + MMA_OFFSET, (uint32_t)MMA_BYTES, &mbar);
 
     const int lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
-    const int ec[2] = {2 * t4, 2 * t4 + 1};                       // the two vector components of this lane
-    const bool xs[2] = {ec[0] < n, ec[1] < n};                    // state component
-    const bool us[2] = {ec[0] >= n && ec[0] < nm, ec[1] >= n && ec[1] < nm};   // input component
+    const int cc[2] = {2 * t4, 2 * t4 + 1};                       // the two columns of this lane
+    const int xe[2] = {T->xat[cc[0]], T->xat[cc[1]]};             // component of x they hold (or -1) ...
+    const int ue[2] = {T->uat[cc[0]], T->uat[cc[1]]};             // ... component of u (or -1)
+    const bool xs[2] = {xe[0] >= 0, xe[1] >= 0};
+    const bool us[2] = {ue[0] >= 0, ue[1] >= 0};
     const unsigned gmask = 0xFu << (4 * g);
     const bool leader = t4 == 0;
+    const bool lo2 = t4 < 2;                                      // MERGE: lanes whose register 1 holds x_4.. (the others: second copies)
 
     const double2 nabt = mma_mat(T->SNABt, lane), nab = mma_mat(T->NAB, lane);
-    double qri[2], qs[2], ts[2], lb[2], ub[2];
+    double qri[2], qriy[2], qs[2], ts[2], lb[2], ub[2];
 #if SPCIES_TERMINAL
     double ti[2];
 #endif
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-        qri[i] = T->QRi[ec[i]];
-        qs[i] = T->Qs[ec[i]];
-        ts[i] = T->Ts[ec[i]];
+        qri[i] = T->QRiz[cc[i]];
+        qriy[i] = T->QRiy[cc[i]];
+        qs[i] = T->Qs[cc[i]];
+        ts[i] = T->Ts[cc[i]];
 #if SPCIES_TERMINAL
-        ti[i] = T->Ti[ec[i]];
+        ti[i] = T->Ti[cc[i]];
 #endif
-        lb[i] = T->LBs[1][ec[i]];
-        ub[i] = T->UBs[1][ec[i]];
+        lb[i] = T->LBs[1][cc[i]];
+        ub[i] = T->UBs[1][cc[i]];
     }
     // bounds of stage row s (0: u_0, 1..N-1: stage s-1, N: terminal)
     auto bnd = [&](int s, int i, double &lo, double &hi) {
 #ifdef VAR_BOUNDS
         if (!VARB) {
-            lo = T->LBs[s][ec[i]];
-            hi = T->UBs[s][ec[i]];
+            lo = T->LBs[s][cc[i]];
+            hi = T->UBs[s][cc[i]];
             return;
         }
 #endif
@@ -221,18 +296,18 @@ __global__ void __launch_bounds__(MMA_BLOCK, 1) fista_mma_kernel(const BatchIO i
                     inst = resume ? __double_as_longlong(pk[0]) : slot;
 #pragma unroll
                     for (int i = 0; i < 2; ++i) {
-                        const int e = ec[i];
-                        const double xr_ = xs[i] ? io.xr[inst * n + e] : 0.0;
-                        const double ur_ = us[i] ? io.ur[inst * m + (e - n)] : 0.0;
+                        const double xr_ = xs[i] ? io.xr[inst * n + xe[i]] : 0.0;
+                        const double ur_ = us[i] ? io.ur[inst * m + ue[i]] : 0.0;
                         q[i] = qs[i] * (xs[i] ? xr_ : ur_);          // QRi o [Q xr; R ur]
                         qT[i] = ts[i] * xr_;                          // Ti o T xr (lax)  |  xr (equ)
                         if (VARB) {
-                            lb[i] = (e < nm) ? io.LB[inst * nm + e] : -1e300;
-                            ub[i] = (e < nm) ? io.UB[inst * nm + e] : 1e300;
+                            const int ze = xs[i] ? xe[i] : n + ue[i];
+                            lb[i] = (xs[i] || us[i]) ? io.LB[inst * nm + ze] : -1e300;
+                            ub[i] = (xs[i] || us[i]) ? io.UB[inst * nm + ze] : 1e300;
                         }
                         double l0, h0;
                         bnd(0, i, l0, h0);
-                        const double x0_ = xs[i] ? io.x0[inst * n + e] : 0.0;
+                        const double x0_ = xs[i] ? io.x0[inst * n + xe[i]] : 0.0;
                         lo0[i] = xs[i] ? x0_ : l0;
                         hi0[i] = xs[i] ? x0_ : h0;
                     }
@@ -242,8 +317,8 @@ __global__ void __launch_bounds__(MMA_BLOCK, 1) fista_mma_kernel(const BatchIO i
                         for (int l = 0; l < N; ++l)
 #pragma unroll
                             for (int i = 0; i < 2; ++i) {
-                                y[l][i] = xs[i] ? pk[(3 + l * n + ec[i]) * io.park_in_cap] : 0.0;
-                                lam[l][i] = xs[i] ? pk[(3 + N * n + l * n + ec[i]) * io.park_in_cap] : 0.0;
+                                y[l][i] = xs[i] ? pk[(3 + l * n + xe[i]) * io.park_in_cap] : 0.0;
+                                lam[l][i] = xs[i] ? pk[(3 + N * n + l * n + xe[i]) * io.park_in_cap] : 0.0;
                             }
                     } else {
                         k = -1;                                       // the warm-up pass brings it to 0
@@ -286,7 +361,7 @@ __global__ void __launch_bounds__(MMA_BLOCK, 1) fista_mma_kernel(const BatchIO i
             for (int i = 0; i < 2; ++i) {
                 double lo, hi;
                 bnd(l + 1, i, lo, hi);
-                zz[l + 1][i] = clip(PRESCALE ? fma(qri[i], y[l][i], zz[l + 1][i]) : (zz[l + 1][i] + y[l][i]) * qri[i], lo, hi);   // z_l  :494-519
+                zz[l + 1][i] = clip(PRESCALE ? fma(qriy[i], y[l][i], zz[l + 1][i]) : (zz[l + 1][i] + y[l][i]) * qri[i], lo, hi);   // z_l  :494-519
             }
 #if SPCIES_TERMINAL
 #pragma unroll
@@ -311,19 +386,32 @@ __global__ void __launch_bounds__(MMA_BLOCK, 1) fista_mma_kernel(const BatchIO i
         bool over = false;
 #pragma unroll
         for (int l = 0; l < N; ++l) over = over || (fabs(r[l][0]) > tolv[0]) || (fabs(r[l][1]) > tolv[1]);
-        // forward step: mu_l = Linv_l r_l - F_l mu_{l-1};  w_l = Uinv_l mu_l
-        double sl[N][2];
-        {
+        // forward step: mu_l = Linv_l r_l - F_l mu_{l-1}   [plain layout: and w_l = Uinv_l mu_l, stored in w]
+        if constexpr (MERGE) {
+            // w[l] keeps mu_l.  Per stage: e_l = Linv r (full k-step, issued ahead), f = e_l - F mu_{l-1} (full k-step),
+            // mu_l = f + [Linv | -F] (r_l, mu_{l-1}) (the shared k-step)
             double e[N][2];
-            double2 li[N];
 #pragma unroll
-            for (int l = 0; l < N; ++l) li[l] = mma_mat(T->Linv[l], lane);
+            for (int l = 0; l < N; ++l) dmma(e[l][0], e[l][1], r[l][0], T->FWa[l][lane].x, 0.0, 0.0);
+            dmma(w[0][0], w[0][1], r[0][1], T->FWb[0][lane], e[0][0], e[0][1]);
 #pragma unroll
-            for (int l = 0; l < N; ++l) dmma(e[l][0], e[l][1], r[l][0], li[l].x, 0.0, 0.0);
+            for (int l = 1; l < N; ++l) {
+                double f0, f1;
+                dmma(f0, f1, w[l - 1][0], T->FWa[l][lane].y, e[l][0], e[l][1]);
+                dmma(w[l][0], w[l][1], lo2 ? r[l][1] : w[l - 1][1], T->FWb[l][lane], f0, f1);
+            }
+        } else {
+            double sl[N][2];
+            {
+                double e[N][2];
+                double2 li[N];
 #pragma unroll
-            for (int l = 0; l < N; ++l) dmma(sl[l][0], sl[l][1], r[l][1], li[l].y, e[l][0], e[l][1]);
-        }
-        {
+                for (int l = 0; l < N; ++l) li[l] = mma_mat(T->Linv[l], lane);
+#pragma unroll
+                for (int l = 0; l < N; ++l) dmma(e[l][0], e[l][1], r[l][0], li[l].x, 0.0, 0.0);
+#pragma unroll
+                for (int l = 0; l < N; ++l) dmma(sl[l][0], sl[l][1], r[l][1], li[l].y, e[l][0], e[l][1]);
+            }
             double mu[2] = {sl[0][0], sl[0][1]};
 #pragma unroll
             for (int l = 1; l < N; ++l) {
@@ -349,7 +437,7 @@ __global__ void __launch_bounds__(MMA_BLOCK, 1) fista_mma_kernel(const BatchIO i
             if (ef != 0) {
 #pragma unroll
                 for (int i = 0; i < 2; ++i)
-                    if (us[i]) io.u[inst * m + (ec[i] - n)] = u0v[i];
+                    if (us[i]) io.u[inst * m + ue[i]] = u0v[i];
                 if (leader) {
                     io.k[inst] = k;
                     io.e[inst] = ef;
@@ -362,17 +450,36 @@ __global__ void __launch_bounds__(MMA_BLOCK, 1) fista_mma_kernel(const BatchIO i
 
         // ================= pass B: backward step, lambda and y updates      :368-385, :619-648 =================
         const double beta = T->beta[(live && k > 0) ? k : 0];
-        double d[2] = {w[N - 1][0], w[N - 1][1]};
-#pragma unroll
-        for (int l = N - 1; l >= 0; --l) {
-            if (l < N - 1) {
-                mma_mv(d, mma_mat(T->NG[l], lane), d, w[l][0], w[l][1]);   // d_lambda_l = w_l - G_l d_lambda_{l+1}
-            }
+        auto update = [&](int l, const double (&d)[2]) {
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
                 const double ln = y[l][i] + d[i];                   // lambda_l = y_l + d_lambda_l
                 y[l][i] = fma(beta, ln - lam[l][i], ln);            // y_l = lambda_l + beta (lambda_l - lambda1_l)
                 lam[l][i] = ln;
+            }
+        };
+        if constexpr (MERGE) {
+            // d_lambda_l = Uinv_l mu_l - G_l d_lambda_{l+1}:  g_l = Uinv mu (full k-step, issued one stage ahead),
+            // h = g_l - G d_{l+1} (full k-step), d_l = h + [Uinv | -G] (mu_l, d_{l+1}) (the shared k-step)
+            double d[2], g0, g1, gn0 = 0.0, gn1 = 0.0;
+            dmma(g0, g1, w[N - 1][0], T->BWa[N - 1][lane].x, 0.0, 0.0);
+            if (N > 1) dmma(gn0, gn1, w[N - 2][0], T->BWa[N - 2][lane].x, 0.0, 0.0);
+            dmma(d[0], d[1], w[N - 1][1], T->BWb[N - 1][lane], g0, g1);
+            update(N - 1, d);
+#pragma unroll
+            for (int l = N - 2; l >= 0; --l) {
+                double h0, h1;
+                dmma(h0, h1, d[0], T->BWa[l][lane].y, gn0, gn1);
+                if (l > 0) dmma(gn0, gn1, w[l - 1][0], T->BWa[l - 1][lane].x, 0.0, 0.0);
+                dmma(d[0], d[1], lo2 ? w[l][1] : d[1], T->BWb[l][lane], h0, h1);
+                update(l, d);
+            }
+        } else {
+            double d[2] = {w[N - 1][0], w[N - 1][1]};
+#pragma unroll
+            for (int l = N - 1; l >= 0; --l) {
+                if (l < N - 1) mma_mv(d, mma_mat(T->NG[l], lane), d, w[l][0], w[l][1]);   // d_lambda_l = w_l - G_l d_lambda_{l+1}
+                update(l, d);
             }
         }
 
@@ -406,8 +513,8 @@ __global__ void __launch_bounds__(MMA_BLOCK, 1) fista_mma_kernel(const BatchIO i
 #pragma unroll
                     for (int i = 0; i < 2; ++i)
                         if (xs[i]) {
-                            pk[(3 + l * n + ec[i]) * io.park_cap] = y[l][i];
-                            pk[(3 + N * n + l * n + ec[i]) * io.park_cap] = lam[l][i];
+                            pk[(3 + l * n + xe[i]) * io.park_cap] = y[l][i];
+                            pk[(3 + N * n + l * n + xe[i]) * io.park_cap] = lam[l][i];
                         }
                 live = false;
             }

@@ -117,6 +117,24 @@ def run_microbench():
         return {'error': str(ex)}
 
 
+def ncu_traffic(launches_per_step):
+    """DRAM bytes (read + write) of one step from the committed `ncu --set full` summary of the same command
+    (profiles/r1_fista_mma_ncu_summary.txt, written by tools/ncu_summary.py): sum over the launches of one step."""
+    p = os.path.join(ROOT, 'profiles', 'r1_fista_mma_ncu_summary.txt')
+    if not os.path.exists(p):
+        return None
+    per_kernel, cur = [], None
+    for ln in open(p):
+        if ln.startswith('====='):
+            cur = 0.0
+            per_kernel.append(cur)
+        elif 'dram__bytes_read.sum' in ln or 'dram__bytes_write.sum' in ln:
+            per_kernel[-1] += float(ln.split()[-1]) * 1e6          # ncu prints Mbyte
+    if len(per_kernel) < launches_per_step or launches_per_step <= 0:
+        return None
+    return sum(per_kernel[:launches_per_step])
+
+
 def measured_peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
@@ -312,12 +330,14 @@ def main():
     fp64_peak = 2.0 * max(micro.get('fp64_tfma_per_s', 0.0), micro.get('fp64_dmma_tfma_per_s', 0.0)) if micro and 'fp64_tfma_per_s' in micro else None
     io_bytes = B * (8 * (2 * n + m) + 8 * m + 8)
     roofline = {'bound': 'fp64_fma', 'achieved': achieved_tflops, 'peak': fp64_peak, 'unit': 'TFLOP/s',
-                'frac': (achieved_tflops / fp64_peak) if fp64_peak else None, 'traffic': None,
+                'frac': (achieved_tflops / fp64_peak) if fp64_peak else None,
                 'peak_source': 'measured in this run by spcies_b200/csrc/microbench.cu (register-only DMMA.8x8x4 / DFMA, full chip, '
                                'whichever is higher); MEASURED_PEAKS.json has no FP64 figure',
                 'kernel': 'spcies::fista::fista_mma_kernel (per step: %d launches = iteration-cap rounds; algorithmic FMA = SURVEY 8(d) '
                           'count of the reference algorithm, not the padded 8x8x4 MMA slots)' % infos[-1]['launches'],
-                'kernel_ms': kernel_ms, 'traffic': None,
+                'kernel_ms': kernel_ms, 'traffic': ncu_traffic(infos[-1]['launches']),
+                'traffic_source': 'dram__bytes_read.sum + dram__bytes_write.sum over the launches of one step, ncu --set full capture of '
+                                  'this command (profiles/r1_fista_mma_ncu_summary.txt); algorithmic batch I/O is roofline.hbm',
                 'algorithmic_fma_per_launch': fma, 'sum_k_per_launch': sum_k,
                 'hbm': {'bound': 'hbm', 'achieved': io_bytes / (kernel_ms * 1e-3) / 1e9, 'peak': peaks['hbm_gbs'],
                         'unit': 'GB/s', 'frac': io_bytes / (kernel_ms * 1e-3) / 1e9 / peaks['hbm_gbs'],

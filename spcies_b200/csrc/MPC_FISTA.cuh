@@ -748,9 +748,9 @@ struct Traits {
     static void engine_shape(int arith, const BatchIO &io, int &block, size_t &smem, int &ipb) {
         ipb = block;
         if (use_mma(arith, io)) {
-            block = MMA_BLOCK;
+            block = (io.phase != 2 && io.B >= MMA_BULK_MIN) ? MMA_BLOCK_BULK : MMA_BLOCK;
             smem = MMA_BYTES;
-            ipb = MMA_IPB;
+            ipb = block / 4;
         }
     }
     static cudaError_t init_device_symbols() {
@@ -802,10 +802,12 @@ struct Traits {
         if (io.engine == SPCIES_CUDA_ENGINE_MMA && !use_mma(arith, io)) return cudaErrorNotSupported;
         if constexpr (HAS_MMA) {
             if (use_mma(arith, io)) {
-                auto kern = varb ? fista_mma_kernel<true> : fista_mma_kernel<false>;
+                auto kern = block == MMA_BLOCK_BULK ? (varb ? fista_mma_kernel<true, MMA_BLOCK_BULK> : fista_mma_kernel<false, MMA_BLOCK_BULK>)
+                                                    : (varb ? fista_mma_kernel<true, MMA_BLOCK> : fista_mma_kernel<false, MMA_BLOCK>);
+                if (block != MMA_BLOCK_BULK && block != MMA_BLOCK) return cudaErrorInvalidConfiguration;
                 cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MMA_BYTES);
                 if (e != cudaSuccess) return e;
-                kern<<<grid, MMA_BLOCK, MMA_BYTES, s>>>(io, (const unsigned char *)dc);
+                kern<<<grid, block, MMA_BYTES, s>>>(io, (const unsigned char *)dc);
                 return cudaGetLastError();
             }
         }
@@ -819,7 +821,7 @@ struct Traits {
     static cudaError_t attributes(int arith, bool varb, cudaFuncAttributes *a) {
         const bool ex = arith == SPCIES_CUDA_ARITH_EXACT;
         if constexpr (HAS_MMA) {
-            if (!ex) return varb ? cudaFuncGetAttributes(a, fista_mma_kernel<true>) : cudaFuncGetAttributes(a, fista_mma_kernel<false>);
+            if (!ex) return varb ? cudaFuncGetAttributes(a, fista_mma_kernel<true, MMA_BLOCK>) : cudaFuncGetAttributes(a, fista_mma_kernel<false, MMA_BLOCK>);
         }
         if (varb)
             return ex ? cudaFuncGetAttributes(a, fista_kernel<true, true, BLOCK1_VARB, USE_TMEM>)

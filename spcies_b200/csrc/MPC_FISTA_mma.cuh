@@ -39,11 +39,16 @@
 #define SPCIES_FISTA_MMA_MERGE 1     // 1: permuted component layout that lets two n-vector products share a k-step (5 <= nn_ <= 6)
 #endif
 #ifndef SPCIES_FISTA_MMA_BLOCK
-#define SPCIES_FISTA_MMA_BLOCK 256
+#define SPCIES_FISTA_MMA_BLOCK 256   // threads per CTA: 2 warps per SM scheduler, up to 255 registers (the low-latency configuration)
+#endif
+#ifndef SPCIES_FISTA_MMA_BLOCK_BULK
+#define SPCIES_FISTA_MMA_BLOCK_BULK 384   // first launch of a large batch: 3 warps per scheduler at 168 registers (a few spills) keep the
+                                          // FP64 pipe busier; resumed rounds and small batches are latency bound and use MMA_BLOCK
 #endif
 
 constexpr int MMA_BLOCK = SPCIES_FISTA_MMA_BLOCK;
-constexpr int MMA_IPB = MMA_BLOCK / 4;                    // instances resident per CTA
+constexpr int MMA_BLOCK_BULK = SPCIES_FISTA_MMA_BLOCK_BULK;
+constexpr long long MMA_BULK_MIN = 16LL * 148 * (MMA_BLOCK_BULK / 4);   // batches of at least 16 waves use the bulk configuration
 constexpr bool HAS_MMA = SPCIES_FISTA_MMA != 0 && sizeof(real) == 8 && nm <= 8 && N >= 2 && N <= 12;
 constexpr int MMA_KTAB = k_max + 2;
 constexpr bool PRESCALE = SPCIES_FISTA_MMA_PRESCALE != 0;
@@ -211,8 +216,8 @@ __device__ __forceinline__ void mma_mv(double (&out)[2], const double2 M, const 
 }
 __device__ __forceinline__ double2 mma_mat(const double *M, int lane) { return reinterpret_cast<const double2 *>(M)[lane]; }
 
-template <bool VARB>
-__global__ void __launch_bounds__(MMA_BLOCK, 1) fista_mma_kernel(const BatchIO io, const unsigned char *__restrict__ g_blob) {
+template <bool VARB, int BLOCK>
+__global__ void __launch_bounds__(BLOCK, 1) fista_mma_kernel(const BatchIO io, const unsigned char *__restrict__ g_blob) {
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint64_t mbar;

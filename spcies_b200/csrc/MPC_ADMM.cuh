@@ -18,6 +18,7 @@
 // cons_equMPC_ADMM_C.m / cons_laxMPC_ADMM_C.m / cons_ellipMPC_ADMM_C.m.
 #pragma once
 #include "spcies_kernel.cuh"
+#include "spcies_mma.cuh"
 
 namespace spcies {
 namespace admm {
@@ -440,8 +441,67 @@ struct Solver {
     };
 };
 
+#include "MPC_ADMM_mma.cuh"
+
+// Host-side traits: the scalar skeleton plus the tensor-core engine (equMPC, FAST arithmetic, no debug payload)
+struct Traits : PolicyTraits<Solver> {
+    typedef PolicyTraits<Solver> Base;
+#if SPCIES_ADMM_MMA_ELIGIBLE
+    static bool &mma_ok() {
+        static bool ok = false;   // set by fill_blob(): the generated constants are uniform over the horizon
+        return ok;
+    }
+    static size_t blob_bytes() { return HAS_MMA ? MMA_OFFSET + MMA_BYTES : Base::blob_bytes(); }
+    static void fill_blob(void *dst) {
+        memset(dst, 0, blob_bytes());
+        Base::fill_blob(dst);
+        if constexpr (HAS_MMA) {
+            MmaTables *T = new MmaTables;
+            mma_ok() = fill_mma_tables(spcies_h_consts, *T);
+            memcpy((char *)dst + MMA_OFFSET, T, sizeof *T);
+            delete T;
+        }
+    }
+    static bool use_mma(int arith, const BatchIO &io) {
+        if constexpr (!HAS_MMA) return false;
+        return mma_ok() && arith != SPCIES_CUDA_ARITH_EXACT && io.sol == nullptr && io.engine != SPCIES_CUDA_ENGINE_SCALAR;
+    }
+    static void engine_shape(int arith, const BatchIO &io, int &block, size_t &smem, int &ipb) {
+        ipb = block;
+        if (use_mma(arith, io)) {
+            block = MMA_BLOCK;
+            smem = MMA_SMEM;
+            ipb = MMA_IPB;
+        }
+    }
+    static cudaError_t launch(int arith, bool varb, int grid, int block, size_t smem, cudaStream_t s, const BatchIO &io,
+                              const void *dc, void *scratch) {
+        if (io.engine == SPCIES_CUDA_ENGINE_MMA && !use_mma(arith, io)) return cudaErrorNotSupported;
+        if constexpr (HAS_MMA) {
+            if (use_mma(arith, io)) {
+                auto kern = varb ? admm_mma_kernel<true> : admm_mma_kernel<false>;
+                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MMA_SMEM);
+                if (e != cudaSuccess) return e;
+                kern<<<grid, MMA_BLOCK, MMA_SMEM, s>>>(io, (const unsigned char *)dc);
+                return cudaGetLastError();
+            }
+        }
+        BatchIO io2 = io;
+        io2.engine = SPCIES_CUDA_ENGINE_AUTO;
+        return Base::launch(arith, varb, grid, block, smem, s, io2, dc, scratch);
+    }
+    static cudaError_t attributes(int arith, bool varb, cudaFuncAttributes *a) {
+        if constexpr (HAS_MMA) {
+            if (mma_ok() && arith != SPCIES_CUDA_ARITH_EXACT)
+                return varb ? cudaFuncGetAttributes(a, admm_mma_kernel<true>) : cudaFuncGetAttributes(a, admm_mma_kernel<false>);
+        }
+        return Base::attributes(arith, varb, a);
+    }
+#endif
+};
+
 }  // namespace admm
 }  // namespace spcies
 
-#define SPCIES_TRAITS ::spcies::PolicyTraits<::spcies::admm::Solver>
+#define SPCIES_TRAITS ::spcies::admm::Traits
 #include "spcies_entry.cuh"

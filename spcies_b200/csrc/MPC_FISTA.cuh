@@ -58,6 +58,7 @@
 #pragma once
 #include "spcies_host.cuh"
 #include "spcies_tmem.cuh"
+#include "spcies_mma.cuh"
 
 // Compile-time switches (set by the generator / tools/variants.py)
 #ifndef SPCIES_FISTA_TMEM

@@ -27,6 +27,7 @@
 // identical, |dk| <= 1).  EXACT mode, float precision, the debug payload and problems with nn_ + mm_ > 8 use the
 // one-thread-per-instance kernel.  Refill is per lane group; park & resume (io.phase) use the same record format.
 #pragma once
+// (spcies_mma.cuh is included by the parent header, outside its namespace)
 
 #ifndef SPCIES_FISTA_MMA
 #define SPCIES_FISTA_MMA 1           // 0: never use the tensor-core engine
@@ -202,17 +203,10 @@ static inline void fill_mma_tables(const spcies_consts &C, const FistaDerived &D
     }
 }
 
-// D = A B + C on one k-step (4 components) of the 8 instances of the warp
-__device__ __forceinline__ void dmma(double &d0, double &d1, const double a, const double b, const double c0, const double c1) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};\n"
-                 : "=d"(d0), "=d"(d1)
-                 : "d"(a), "d"(b), "d"(c0), "d"(c1));
-}
+using mma::dmma;
 // out = c + M v   (M = the lane's double2 of the row-major 8 x 8 matrix; out may alias c)
 __device__ __forceinline__ void mma_mv(double (&out)[2], const double2 M, const double (&v)[2], const double c0, const double c1) {
-    double e0, e1;
-    dmma(e0, e1, v[0], M.x, c0, c1);
-    dmma(out[0], out[1], v[1], M.y, e0, e1);
+    mma::mv(out, M, v, c0, c1);
 }
 __device__ __forceinline__ double2 mma_mat(const double *M, int lane) { return reinterpret_cast<const double2 *>(M)[lane]; }
 

@@ -147,6 +147,7 @@ template <class S> struct PolicyTraits {
     }
     static cudaError_t launch(int arith, bool varb, int grid, int block, size_t smem, cudaStream_t s, const BatchIO &io,
                               const void *dc, void *scratch) {
+        if (io.engine == SPCIES_CUDA_ENGINE_MMA) return cudaErrorNotSupported;   // this skeleton is the scalar engine
         if (block != default_block(varb)) return cudaErrorInvalidConfiguration;
         const bool ex = arith == SPCIES_CUDA_ARITH_EXACT;
         if (varb) {

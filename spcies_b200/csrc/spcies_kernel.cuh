@@ -27,7 +27,10 @@ namespace spcies {
 constexpr size_t SMEM_MAX_BYTES = 227 * 1024;
 constexpr size_t MAX_SMEM_CONSTS = 64 * 1024;
 constexpr int MIN_SMEM_THREADS = 64;
-constexpr int GLOBAL_STATE_BLOCK = 128;
+#ifndef SPCIES_GLOBAL_STATE_BLOCK
+#define SPCIES_GLOBAL_STATE_BLOCK 128
+#endif
+constexpr int GLOBAL_STATE_BLOCK = SPCIES_GLOBAL_STATE_BLOCK;   // threads per CTA when the iterates live in the global scratch
 
 template <typename T, int STRIDE_CT> struct StateRef {
     // STRIDE_CT > 0: shared memory with a compile-time stride (= block size); 0: global memory, run-time stride

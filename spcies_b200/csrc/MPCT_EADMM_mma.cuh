@@ -9,7 +9,7 @@
 // With one thread per instance the 12.5 KB of iterates of an N = 50 instance (BASELINE.json configs[4]) only fit a global
 // scratch; here z1, z3, lambda and the forward-substituted mu' live in shared memory as [block][lane] double2 (4 N + 5 blocks,
 // 105 KB per warp at N = 50 -> two warps per SM), the per-stage component constants (rho, H1i, H3i) as one 64-byte row per
-// stage, and the recurrence fragments are streamed from global memory (L2) one stage ahead when they do not fit beside the
+// stage, and the recurrence fragments are streamed from global memory (L2) PF stages ahead when they do not fit beside the
 // iterates.
 //
 // Arithmetic: FAST (FMA, explicit block inverses, dot products in the MMA's order, q2 accumulated in two interleaved partial
@@ -22,6 +22,7 @@
 #endif
 
 constexpr bool MMA_SHAPE_OK = n >= 5 && n <= 6 && nm <= 8 && N >= 3;
+constexpr int PF = 4;                                             // prefetch distance (stages) of the recurrence fragments
 constexpr int MMA_NBLK = 4 * N + 5;                               // z1[N+1], z3[N+1], lambda[N+3], mu'[N]
 constexpr int BLK_Z1 = 0, BLK_Z3 = N + 1, BLK_LAM = 2 * N + 2, BLK_MUP = 3 * N + 5;
 constexpr size_t MMA_STATE_PER_WARP = (size_t)MMA_NBLK * 32 * sizeof(double2);
@@ -235,23 +236,35 @@ __global__ void __launch_bounds__(MMA_BLOCK, 1) eadmm_mma_kernel(const BatchIO i
         {
             double ta[2], tb[2], mup[2] = {0.0, 0.0};
             t_of(0, ta);
-            double2 fa = FWA(0);
-            double fb = FWB(0);
+            // the recurrence fragments are fetched PF stages ahead into a register ring (they stream from L2 when they do
+            // not fit shared memory; the ring index is static because the stage loop is unrolled by PF)
+            double2 fa[PF];
+            double fb[PF];
+#pragma unroll
+            for (int j = 0; j < PF; ++j) {
+                fa[j] = FWA(j < N ? j : N - 1);
+                fb[j] = FWB(j < N ? j : N - 1);
+            }
 #pragma unroll 1
-            for (int l = 0; l < N; ++l) {
-                const double2 fan = FWA(l + 1 < N ? l + 1 : l);      // one stage ahead (global-memory fragments)
-                const double fbn = FWB(l + 1 < N ? l + 1 : l);
-                t_of(l + 1, tb);
-                double r[2], e0, e1, f0, f1;
-                mma::mv(r, nab, ta, tb[0], tb[1]);
-                dmma(e0, e1, r[0], fa.x, 0.0, 0.0);
-                dmma(f0, f1, mup[0], fa.y, e0, e1);                  // F_0 = 0
-                dmma(mup[0], mup[1], lo2 ? r[1] : mup[1], fb, f0, f1);
-                ST(BLK_MUP + l, make_double2(mup[0], mup[1]));
-                ta[0] = tb[0];
-                ta[1] = tb[1];
-                fa = fan;
-                fb = fbn;
+            for (int l0 = 0; l0 < N; l0 += PF) {
+#pragma unroll
+                for (int j = 0; j < PF; ++j) {
+                    const int l = l0 + j;
+                    if (l < N) {
+                        t_of(l + 1, tb);
+                        double r[2], e0, e1, f0, f1;
+                        mma::mv(r, nab, ta, tb[0], tb[1]);
+                        dmma(e0, e1, r[0], fa[j].x, 0.0, 0.0);
+                        dmma(f0, f1, mup[0], fa[j].y, e0, e1);               // F_0 = 0
+                        dmma(mup[0], mup[1], lo2 ? r[1] : mup[1], fb[j], f0, f1);
+                        ST(BLK_MUP + l, make_double2(mup[0], mup[1]));
+                        ta[0] = tb[0];
+                        ta[1] = tb[1];
+                        const int ln = l + PF < N ? l + PF : N - 1;
+                        fa[j] = FWA(ln);
+                        fb[j] = FWB(ln);
+                    }
+                }
             }
         }
         // ---------- P3 backward + z3 + residual + lambda + exit tests                      :254-320, :371-449
@@ -285,29 +298,39 @@ __global__ void __launch_bounds__(MMA_BLOCK, 1) eadmm_mma_kernel(const BatchIO i
                 z3n[1] = -h3.y * fma(-maskx[1], mu[1], q[1]);
                 close_stage(N, z3n);
             }
-            double2 ba = BWA(N > 1 ? N - 2 : 0);
-            double bb = BWB(N > 1 ? N - 2 : 0);
+            double2 ba[PF];
+            double bb[PF];
+#pragma unroll
+            for (int j = 0; j < PF; ++j) {
+                ba[j] = BWA(N - 2 - j >= 0 ? N - 2 - j : 0);
+                bb[j] = BWB(N - 2 - j >= 0 ? N - 2 - j : 0);
+            }
 #pragma unroll 1
-            for (int l = N - 2; l >= 0; --l) {
-                const double2 ban = BWA(l > 0 ? l - 1 : 0);
-                const double bbn = BWB(l > 0 ? l - 1 : 0);
-                const double2 mp = LD(BLK_MUP + l);
-                double g0, g1, h0, h1;
-                dmma(g0, g1, mp.x, ba.x, 0.0, 0.0);
-                dmma(h0, h1, mu[0], ba.y, g0, g1);
-                dmma(mun[0], mun[1], lo2 ? mp.y : mu[1], bb, h0, h1);
-                // z3_{l+1} = -H3i_{l+1} o (q3_{l+1} - [mu_l; 0] + [A B]' mu_{l+1})
-                double q[2], a[2], z3n[2];
-                q3_of(l + 1, q);
-                mma::mv(a, abt, mu, fma(-maskx[0], mun[0], q[0]), fma(-maskx[1], mun[1], q[1]));
-                const double2 h3 = ROW(T->H3i, l + 1);
-                z3n[0] = -h3.x * a[0];
-                z3n[1] = -h3.y * a[1];
-                close_stage(l + 1, z3n);
-                mu[0] = mun[0];
-                mu[1] = mun[1];
-                ba = ban;
-                bb = bbn;
+            for (int l0 = N - 2; l0 >= 0; l0 -= PF) {
+#pragma unroll
+                for (int j = 0; j < PF; ++j) {
+                    const int l = l0 - j;
+                    if (l >= 0) {
+                        const double2 mp = LD(BLK_MUP + l);
+                        double g0, g1, h0, h1;
+                        dmma(g0, g1, mp.x, ba[j].x, 0.0, 0.0);
+                        dmma(h0, h1, mu[0], ba[j].y, g0, g1);
+                        dmma(mun[0], mun[1], lo2 ? mp.y : mu[1], bb[j], h0, h1);
+                        // z3_{l+1} = -H3i_{l+1} o (q3_{l+1} - [mu_l; 0] + [A B]' mu_{l+1})
+                        double q[2], a[2], z3n[2];
+                        q3_of(l + 1, q);
+                        mma::mv(a, abt, mu, fma(-maskx[0], mun[0], q[0]), fma(-maskx[1], mun[1], q[1]));
+                        const double2 h3 = ROW(T->H3i, l + 1);
+                        z3n[0] = -h3.x * a[0];
+                        z3n[1] = -h3.y * a[1];
+                        close_stage(l + 1, z3n);
+                        mu[0] = mun[0];
+                        mu[1] = mun[1];
+                        const int ln = l - PF >= 0 ? l - PF : 0;
+                        ba[j] = BWA(ln);
+                        bb[j] = BWB(ln);
+                    }
+                }
             }
             {   // z3_0 = -H3i_0 o (q3_0 + [A B]' mu_0)
                 double q[2], a[2], z3n[2];

@@ -21,8 +21,8 @@ CONFIGS = {
     'C2_laxMPC_FISTA': (1 << 20, 1 << 15),
     'C3_equMPC_ADMM': (1 << 18, 2048),
     'C4_ellipMPC_ADMM_soc': (1 << 17, 512),
-    'C5b_MPCT_EADMM': (1 << 16, 1024),
-    'C5a_HMPC_SADMM_split': (1 << 12, 24),
+    'C5b_MPCT_EADMM': (1 << 17, 1024),
+    'C5a_HMPC_SADMM_split': (1 << 15, 24),
 }
 
 

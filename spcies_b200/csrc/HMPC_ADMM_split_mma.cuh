@@ -28,9 +28,17 @@ constexpr int NT = ZT + 3;                        // + y_e, y_s, y_c
 constexpr int NIN = NT + 1;                       // input tiles of the product: q_hat, then bh
 constexpr int NCLIP = DIM - 3 * n - 3 * m;        // clipped entries of z (:233)
 constexpr int QT0 = Q0 / 8, QT1 = (Q0 + 3 * n + m - 1) / 8, QTN = QT1 - QT0 + 1;   // tiles that hold non-zeros of q
-constexpr int PF = 4;                             // prefetch distance of the fragment stream (input tiles)
+#ifndef SPCIES_HMPC_MMA_NB
+#define SPCIES_HMPC_MMA_NB 4                      // output tiles per pass over q_hat (independent accumulators)
+#endif
+#ifndef SPCIES_HMPC_MMA_PF
+#define SPCIES_HMPC_MMA_PF 8                      // prefetch distance of the fragment stream (input tiles): PF x NB x 32 cycles of MMA
+#endif                                            // issue must cover the L2 latency; the ring is PF x NB x 512 B per warp
+constexpr int NBZ = SPCIES_HMPC_MMA_NB, PFZ = SPCIES_HMPC_MMA_PF;
 constexpr bool MMA_SHAPE_OK = NS == 3 * nm && nm <= 8 && n <= 8 && QTN <= 4;
-constexpr size_t MMA_STATE_PER_WARP = (size_t)3 * NT * 32 * sizeof(double2);
+constexpr size_t MMA_RING_PER_WARP = (size_t)PFZ * NBZ * 32 * sizeof(double2);
+constexpr int NST = 3 * NT + 2;                   // primal, dual, q_hat tiles; then bh (the last input tile) and a dummy
+constexpr size_t MMA_STATE_PER_WARP = (size_t)NST * 32 * sizeof(double2) + MMA_RING_PER_WARP;
 constexpr int BLK_P = 0, BLK_D = NT, BLK_QH = 2 * NT;
 
 struct alignas(16) MmaSmall {                     // staged into shared memory
@@ -38,7 +46,7 @@ struct alignas(16) MmaSmall {                     // staged into shared memory
     double LBy[8], UBy[8];
 };
 constexpr size_t SMALL_BYTES = (sizeof(MmaSmall) + 15) / 16 * 16;
-constexpr size_t FRAG_BYTES = (size_t)NT * NIN * 32 * sizeof(double2);   // [-M1 | M2] fragments, global memory
+constexpr size_t FRAG_BYTES = ((size_t)NT * NIN + 16) * 32 * sizeof(double2);   // [-M1 | M2] fragments (+ padding), global memory
 constexpr size_t CONSTS_BYTES_ = (sizeof(spcies_consts) + 15) / 16 * 16;
 constexpr size_t MMA_OFFSET = CONSTS_BYTES_;      // blob: spcies_consts | MmaSmall | fragments
 constexpr size_t SMEM_LIMIT = 227 * 1024 - 64;
@@ -90,35 +98,62 @@ static inline void fill_mma_tables(const spcies_consts &C, MmaSmall &S, double2 
 }
 
 // acc[b] = sum over the NIN input tiles of (fragment of output tile ot + b, input tile it) x (q_hat tile it | bh): NB independent
-// accumulators; the fragments run PF input tiles ahead in a register ring (static ring index: the input loop is unrolled by PF)
-template <int NB>
-__device__ __forceinline__ void hmpc_product(const double2 *__restrict__ fr, const double2 *st, const double (&bh)[2], double (&acc)[NB][2]) {
+// accumulators.  The fragments stream from L2 into a per-warp shared-memory ring with cp.async (LDGSTS), PF input tiles ahead;
+// every lane copies and later reads only its own 16 bytes, so the ring needs no cross-lane synchronisation.
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int K> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(K) : "memory"); }
+
+// The loop is kept free of integer overhead (it was issue bound: 3 IMAD per DMMA): pointers advance by constants, bh is tile NT
+// of the q_hat array (tile NT + 1 is a dummy for the last prefetch), the fragment table is padded by PF tiles so that the refill
+// needs no bound check, and the body is unrolled by two so that the "next -> current" operand hand-over is a renaming.
+template <int NB, int PF>
+__device__ __forceinline__ void hmpc_product(const double2 *__restrict__ fr, const double2 *qh /* q_hat tile 0 of this lane */,
+                                             double2 *ring /* [PF][NB][32], + lane */, double (&acc)[NB][2]) {
     using mma::dmma;
-    double2 ring[PF][NB];
 #pragma unroll
-    for (int j = 0; j < PF; ++j)
+    for (int j = 0; j < PF; ++j) {
 #pragma unroll
-        for (int b = 0; b < NB; ++b) ring[j][b] = __ldg(fr + ((size_t)b * NIN + (j < NIN ? j : NIN - 1)) * 32);
+        for (int b = 0; b < NB; ++b) cp_async16(ring + (j * NB + b) * 32, fr + ((size_t)b * NIN + j) * 32);
+        cp_async_commit();
+    }
 #pragma unroll
     for (int b = 0; b < NB; ++b) acc[b][0] = acc[b][1] = 0.0;
-#pragma unroll 1
-    for (int i0 = 0; i0 < NIN; i0 += PF) {
+    // operands of an input tile (q_hat tile, fragments) are read from shared memory one tile ahead of their MMAs
+    double2 v = qh[0], f[NB];
+    cp_async_wait<PF - 1>();                                               // the group of input tile 0 has landed
 #pragma unroll
-        for (int j = 0; j < PF; ++j) {
-            const int it = i0 + j;
-            if (it < NIN) {
-                double2 v = st[(BLK_QH + (it < NT ? it : 0)) * 32];
-                if (it == NT) v = make_double2(bh[0], bh[1]);
+    for (int b = 0; b < NB; ++b) f[b] = ring[b * 32];
+    const double2 *gnext = fr + PF * 32;                                   // fragments of input tile it + PF
+    const double2 *qn = qh + 32;                                           // q_hat tile it + 1
+    double2 *rcur = ring;                                                  // ring slot of input tile it
+    double2 *const rend = ring + PF * NB * 32;
+#pragma unroll 2
+    for (int it = 0; it < NIN; ++it) {
+        double2 *rnxt = rcur + NB * 32;
+        rnxt = rnxt == rend ? ring : rnxt;
+        const double2 vn = *qn;
+        double2 fn[NB];
+        cp_async_wait<PF - 2>();                                            // ... and the group of input tile it + 1
 #pragma unroll
-                for (int b = 0; b < NB; ++b) dmma(acc[b][0], acc[b][1], v.x, ring[j][b].x, acc[b][0], acc[b][1]);
+        for (int b = 0; b < NB; ++b) fn[b] = rnxt[b * 32];
 #pragma unroll
-                for (int b = 0; b < NB; ++b) dmma(acc[b][0], acc[b][1], v.y, ring[j][b].y, acc[b][0], acc[b][1]);
-                const int itn = it + PF < NIN ? it + PF : NIN - 1;
+        for (int b = 0; b < NB; ++b) dmma(acc[b][0], acc[b][1], v.x, f[b].x, acc[b][0], acc[b][1]);
 #pragma unroll
-                for (int b = 0; b < NB; ++b) ring[j][b] = __ldg(fr + ((size_t)b * NIN + itn) * 32);
-            }
-        }
+        for (int b = 0; b < NB; ++b) dmma(acc[b][0], acc[b][1], v.y, f[b].y, acc[b][0], acc[b][1]);
+#pragma unroll
+        for (int b = 0; b < NB; ++b) cp_async16(rcur + b * 32, gnext + (size_t)b * NIN * 32);
+        cp_async_commit();
+        gnext += 32;
+        qn += 32;
+        rcur = rnxt;
+        v = vn;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) f[b] = fn[b];
     }
+    cp_async_wait<0>();
 }
 
 __global__ void __launch_bounds__(MMA_BLOCK, 1) hmpc_mma_kernel(const BatchIO io, const unsigned char *__restrict__ g_blob) {
@@ -136,6 +171,7 @@ __global__ void __launch_bounds__(MMA_BLOCK, 1) hmpc_mma_kernel(const BatchIO io
     const unsigned gmask = 0xFu << (4 * g);
     const bool leader = t4 == 0;
     double2 *st = reinterpret_cast<double2 *>(smem_raw + SMALL_BYTES + warp * MMA_STATE_PER_WARP) + lane;
+    double2 *ring = st + NST * 32;
     auto LD = [&](int blk) { return st[blk * 32]; };
     auto ST = [&](int blk, double2 v) { st[blk * 32] = v; };
 
@@ -201,6 +237,8 @@ __global__ void __launch_bounds__(MMA_BLOCK, 1) hmpc_mma_kernel(const BatchIO io
                     }
 #pragma unroll 4
                     for (int e = 0; e < 2 * NT; ++e) ST(e, make_double2(0.0, 0.0));
+                    ST(BLK_QH + NT, make_double2(bh[0], bh[1]));
+                    ST(BLK_QH + NT + 1, make_double2(0.0, 0.0));
                     k = 0;
                     live = true;
                 }
@@ -253,21 +291,22 @@ __global__ void __launch_bounds__(MMA_BLOCK, 1) hmpc_mma_kernel(const BatchIO io
         {
             int t = 0;
 #pragma unroll 1
-            for (; t + 2 <= ZT; t += 2) {
-                double acc[2][2];
-                hmpc_product<2>(frag + ((size_t)t * NIN) * 32 + lane, st, bh, acc);
-                update_z(t, acc[0]);
-                update_z(t + 1, acc[1]);
+            for (; t + NBZ <= ZT; t += NBZ) {
+                double acc[NBZ][2];
+                hmpc_product<NBZ, PFZ>(frag + ((size_t)t * NIN) * 32 + lane, st + BLK_QH * 32, ring, acc);
+#pragma unroll
+                for (int b = 0; b < NBZ; ++b) update_z(t + b, acc[b]);
             }
-            if (t < ZT) {
+#pragma unroll 1
+            for (; t < ZT; ++t) {
                 double acc[1][2];
-                hmpc_product<1>(frag + ((size_t)t * NIN) * 32 + lane, st, bh, acc);
+                hmpc_product<1, PFZ>(frag + ((size_t)t * NIN) * 32 + lane, st + BLK_QH * 32, ring, acc);
                 update_z(t, acc[0]);
             }
         }
         {   // s, mu: diamond-set projection of each (y_e, y_s, y_c) triple                              :220-225, :241-258, :294-311
             double acc[3][2];
-            hmpc_product<3>(frag + ((size_t)ZT * NIN) * 32 + lane, st, bh, acc);
+            hmpc_product<3, PFZ>(frag + ((size_t)ZT * NIN) * 32 + lane, st + BLK_QH * 32, ring, acc);
             const double2 so0 = LD(BLK_P + ZT), so1 = LD(BLK_P + ZT + 1), so2 = LD(BLK_P + ZT + 2);
             const double2 mu0 = LD(BLK_D + ZT), mu1 = LD(BLK_D + ZT + 1), mu2 = LD(BLK_D + ZT + 2);
             const double so[3][2] = {{so0.x, so0.y}, {so1.x, so1.y}, {so2.x, so2.y}};

@@ -216,7 +216,18 @@ def main():
         raise SystemExit('bench.py: no CUDA device -- the solver has no CPU fallback')
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+        # NCCL prints its version banner on stdout at the first collective: keep stdout for the one JSON line
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+            dist.barrier()
+            torch.cuda.synchronize(local_rank)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     dev = torch.device('cuda', local_rank)
     sol, spec, cfg = prebuilt.get(save_name)
     n, m = sol.n, sol.m

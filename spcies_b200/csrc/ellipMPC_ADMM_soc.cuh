@@ -16,6 +16,7 @@
 // subtracting the remaining exact zeros of bh is the identity in IEEE arithmetic, so skipping them is bit-exact.
 #pragma once
 #include "spcies_kernel.cuh"
+#include "spcies_mma.cuh"
 #include "spcies_sparse.cuh"
 
 namespace spcies {
@@ -163,8 +164,57 @@ struct Solver {
     };
 };
 
+#include "ellipMPC_ADMM_soc_mma.cuh"
+
+// Host-side traits: the scalar skeleton plus the tensor-core engine (FAST arithmetic, no debug payload)
+struct Traits : PolicyTraits<Solver> {
+    typedef PolicyTraits<Solver> Base;
+    static size_t blob_bytes() { return HAS_MMA ? MMA_OFFSET + SMALL_BYTES + FRAG_BYTES : Base::blob_bytes(); }
+    static void fill_blob(void *dst) {
+        memset(dst, 0, blob_bytes());
+        Base::fill_blob(dst);
+        if constexpr (HAS_MMA) {
+            MmaSmall *S = new MmaSmall;
+            fill_mma_tables(spcies_h_consts, *S, reinterpret_cast<double2 *>((char *)dst + MMA_OFFSET + SMALL_BYTES));
+            memcpy((char *)dst + MMA_OFFSET, S, sizeof *S);
+            delete S;
+        }
+    }
+    static bool use_mma(int arith, const BatchIO &io) {
+        if constexpr (!HAS_MMA) return false;
+        return arith != SPCIES_CUDA_ARITH_EXACT && io.sol == nullptr && io.engine != SPCIES_CUDA_ENGINE_SCALAR && io.LB == nullptr;
+    }
+    static void engine_shape(int arith, const BatchIO &io, int &block, size_t &smem, int &ipb) {
+        ipb = block;
+        if (use_mma(arith, io)) {
+            block = MMA_BLOCK;
+            smem = MMA_SMEM;
+            ipb = MMA_IPB;
+        }
+    }
+    static cudaError_t launch(int arith, bool varb, int grid, int block, size_t smem, cudaStream_t s, const BatchIO &io,
+                              const void *dc, void *scratch) {
+        if (io.engine == SPCIES_CUDA_ENGINE_MMA && !use_mma(arith, io)) return cudaErrorNotSupported;
+        if constexpr (HAS_MMA) {
+            if (use_mma(arith, io)) {
+                cudaError_t e = cudaFuncSetAttribute(soc_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MMA_SMEM);
+                if (e != cudaSuccess) return e;
+                soc_mma_kernel<<<grid, MMA_BLOCK, MMA_SMEM, s>>>(io, (const unsigned char *)dc);
+                return cudaGetLastError();
+            }
+        }
+        return Base::launch(arith, varb, grid, block, smem, s, io, dc, scratch);
+    }
+    static cudaError_t attributes(int arith, bool varb, cudaFuncAttributes *a) {
+        if constexpr (HAS_MMA) {
+            if (arith != SPCIES_CUDA_ARITH_EXACT) return cudaFuncGetAttributes(a, soc_mma_kernel);
+        }
+        return Base::attributes(arith, varb, a);
+    }
+};
+
 }  // namespace soc
 }  // namespace spcies
 
-#define SPCIES_TRAITS ::spcies::PolicyTraits<::spcies::soc::Solver>
+#define SPCIES_TRAITS ::spcies::soc::Traits
 #include "spcies_entry.cuh"

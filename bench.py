@@ -35,19 +35,37 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # config -> (prebuilt solver, per-GPU batch, description)
-    'C2': ('C2_laxMPC_FISTA', 1 << 20, 'laxMPC FISTA oscillating masses N=10, 1Mi random x0/references per GPU'),
+    # config -> (prebuilt solver, per-GPU batch, CPU-baseline sample, description).  C2 is the headline (BASELINE.json configs[1], the
+    # default); the others are the remaining BASELINE configurations, measured under the same contract with --config.
+    'C2': ('C2_laxMPC_FISTA', 1 << 20, 1 << 19, 'laxMPC FISTA oscillating masses N=10, 1Mi random x0/references per GPU'),
+    'C3': ('C3_equMPC_ADMM', 1 << 20, 1 << 14, 'equMPC ADMM oscillating masses N=20, 1Mi-instance batch per GPU, double'),
+    'C4': ('C4_ellipMPC_ADMM_soc', 1 << 20, 1 << 14, 'ellipMPC ADMM_soc (proj_SOC terminal constraint) N=10, 1Mi-instance batch per GPU'),
+    'C5a': ('C5a_HMPC_SADMM_split', 1 << 17, 512, 'HMPC SADMM_split N=50, 128Ki-instance shard per GPU'),
+    'C5b': ('C5b_MPCT_EADMM', 1 << 20, 1 << 14, 'MPCT EADMM N=50, 1Mi-instance shard per GPU'),
 }
+KERNELS = {'laxMPC_FISTA': 'spcies::fista::fista_mma_kernel', 'equMPC_ADMM': 'spcies::admm::admm_mma_kernel',
+           'ellipMPC_ADMM_soc': 'spcies::soc::soc_mma_kernel', 'MPCT_EADMM': 'spcies::eadmm::eadmm_mma_kernel',
+           'HMPC_SADMM_split': 'spcies::hmpc::hmpc_mma_kernel', 'HMPC_ADMM_split': 'spcies::hmpc::hmpc_mma_kernel'}
 
 
-def fma_per_instance(solver_name, dims, sum_k, B):
-    """Algorithmic FMA count: laxMPC FISTA  FMA(k) = (k+1) F_zr + k F_W."""
+def fma_per_instance(solver_name, dims, sum_k, B, spec=None):
+    """Algorithmic FMA count of the reference algorithm, not the padded MMA slots."""
     n, m, N = dims['n'], dims['m'], dims['N']
     nm = n + m
-    if solver_name == 'laxMPC_FISTA':
+    F_W = 2 * (N * n * (n - 1) // 2 + (N - 1) * n * n)          # banded-Cholesky solve, forward + backward
+    if solver_name == 'laxMPC_FISTA':                            # FMA(k) = (k+1) F_zr + k F_W
         F_zr = 2 * (m * n + (N - 1) * n * nm)
-        F_W = 2 * (N * n * (n - 1) // 2 + (N - 1) * n * n)
         return (sum_k + B) * F_zr + sum_k * F_W
+    if solver_name == 'equMPC_ADMM':
+        return sum_k * (F_W + 3 * (N - 1) * n * nm + 2 * m * n)
+    if solver_name == 'ellipMPC_ADMM_soc':
+        nnz = sum(len(np.ravel(spec.const(c))) for c in ('GhHhi_val', 'Hhi_val', 'HhiGh_val')) + 2 * len(np.ravel(spec.const('L_val')))
+        return sum_k * nnz
+    if solver_name == 'MPCT_EADMM':
+        return sum_k * (F_W + 2 * (N + 1) * n * nm + nm * nm)
+    if solver_name in ('HMPC_SADMM_split', 'HMPC_ADMM_split'):
+        NP = dims['dim'] + dims['n_s']
+        return sum_k * (NP * NP + NP * n)
     raise KeyError(solver_name)
 
 
@@ -147,9 +165,11 @@ def cpu_reference_leg(save_name, batch, sample, threads):
     from oracle import refs
     ref = refs.get(save_name)[0]
     x0, xr, ur = batch['x0'][:sample], batch['xr'][:sample], batch['ur'][:sample]
-    ref.solve_batch(x0[:256], xr[:256], ur[:256], threads=1)            # warm the code path
+    kw = {'r': batch['r'][:sample]} if 'r' in batch else {}
+    w = min(sample, 64)
+    ref.solve_batch(x0[:w], xr[:w], ur[:w], threads=1, **({'r': batch['r'][:w]} if 'r' in batch else {}))   # warm the code path
     t0 = time.perf_counter()
-    u, k, e = ref.solve_batch(x0, xr, ur, threads=threads)
+    u, k, e = ref.solve_batch(x0, xr, ur, threads=threads, **kw)
     dt = time.perf_counter() - t0
     return sample / dt, dt, u, k, e
 
@@ -168,7 +188,7 @@ def main():
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
-    save_name, B, desc = WORKLOADS[args.config]
+    save_name, B, cpu_sample, desc = WORKLOADS[args.config]
     if args.batch:
         B = args.batch
     W = max(args.warmup, 3)
@@ -189,8 +209,8 @@ def main():
         if rank != 0:
             return
         cores = os.cpu_count() or 1
-        sample = min(B, 1 << 17)
-        batch = sysmodel.synthetic_batch(cfg['sys'], sample, seed=100)
+        sample = min(B, max(256, cpu_sample // 4))
+        batch = sysmodel.synthetic_batch(cfg['sys'], sample, seed=100, with_r=bool(spec.extra_inputs))
         rates = []
         for i in range(W + K):
             rate, dt, _, k, e = cpu_reference_leg(save_name, batch, sample, cores)
@@ -236,7 +256,7 @@ def main():
     NB = 3
     host, devb = [], []
     for i in range(NB):
-        b = sysmodel.synthetic_batch(cfg['sys'], B, seed=100 + 3 * rank + i)
+        b = sysmodel.synthetic_batch(cfg['sys'], B, seed=100 + 3 * rank + i, with_r=sol.has_r)
         hb = {k: torch.from_numpy(v).pin_memory() for k, v in b.items()}
         host.append(hb)
         devb.append({k: v.to(dev) for k, v in hb.items()})
@@ -251,13 +271,13 @@ def main():
     def step_dev(i):
         b = devb[i % NB]
         return sol.solve_batch_device(B, b['x0'].data_ptr(), b['xr'].data_ptr(), b['ur'].data_ptr(),
-                                      d_u.data_ptr(), d_k.data_ptr(), d_e.data_ptr(),
+                                      d_u.data_ptr(), d_k.data_ptr(), d_e.data_ptr(), d_r=b['r'].data_ptr() if sol.has_r else None,
                                       device=local_rank, stream=stream.cuda_stream)
 
     def step_host(i):
         b = host[i % NB]
-        return sol.solve_batch(b['x0'].numpy(), b['xr'].numpy(), b['ur'].numpy(), device=local_rank,
-                               out=(h_u.numpy(), h_k.numpy(), h_e.numpy()))[3]
+        return sol.solve_batch(b['x0'].numpy(), b['xr'].numpy(), b['ur'].numpy(), r=b['r'].numpy() if sol.has_r else None,
+                               device=local_rank, out=(h_u.numpy(), h_k.numpy(), h_e.numpy()))[3]
 
     def barrier():
         if world > 1:
@@ -309,17 +329,17 @@ def main():
     # ---- parity gate on a subset (every benchmark run) + CPU baseline, rank 0 at N = 1 only
     cpu_baseline, parity = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sample = min(B, 1 << 19)                       # ~13 s on one core (mean k = 32)
+        sample = min(B, cpu_sample)                    # ~10-15 s on one core
         b0 = {k: v.numpy() for k, v in host[(W + K - 1) % NB].items()}
         rate1, dt1, ur_, kr, er = cpu_reference_leg(save_name, b0, sample, 1)
         cores = os.cpu_count() or 1
         rate_all, dt_all, _, _, _ = cpu_reference_leg(save_name, b0, sample, cores)
         u, k, e = h_u.numpy()[:sample], h_k.numpy()[:sample], h_e.numpy()[:sample]
-        same = k == kr
+        same = (k == kr) & (er == 1)                   # converged instances with the same iteration count
         rel = np.abs(u - ur_) / np.maximum(1.0, np.abs(ur_))
         parity = {'compared': int(sample), 'e_flag_mismatch': int((e != er).sum()),
-                  'max_abs_dk': int(np.abs(k - kr).max()), 'n_dk_nonzero': int((~same).sum()),
-                  'u_opt_max_rel_err_same_k': float(rel[same].max()), 'tolerance': 1e-9}
+                  'max_abs_dk': int(np.abs(k - kr).max()), 'n_dk_nonzero': int((k != kr).sum()),
+                  'u_opt_max_rel_err_same_k': float(rel[same].max()) if same.any() else None, 'tolerance': 1e-9}
         cpu_baseline = {'value': rate1, 'unit': 'solves/s', 'cores': 1, 'kind': 'reference',
                         'sample': f'first {sample} instances of the last timed batch; instantiated reference template, '
                                   f'gcc -O3, DEBUG/MEASURE_TIME off; {dt1:.1f} s',
@@ -334,19 +354,19 @@ def main():
 
     micro = run_microbench()
     peaks, peak_kind = measured_peaks()
-    fma = fma_per_instance(spec.options.solver_key(), dims, sum_k, B)
+    fma = fma_per_instance(spec.options.solver_key(), dims, sum_k, B, spec)
     achieved_tflops = 2.0 * fma / (kernel_ms * 1e-3) / 1e12
     # ceiling of the FP64 datapath: the larger of the DFMA and DMMA issue rates measured in this run (the solver's tensor-core
     # engine issues DMMA.8x8x4; both instruction kinds share the pipe)
     fp64_peak = 2.0 * max(micro.get('fp64_tfma_per_s', 0.0), micro.get('fp64_dmma_tfma_per_s', 0.0)) if micro and 'fp64_tfma_per_s' in micro else None
-    io_bytes = B * (8 * (2 * n + m) + 8 * m + 8)
+    io_bytes = B * (8 * (2 * n + m + (1 if sol.has_r else 0)) + 8 * m + 8)
     roofline = {'bound': 'fp64_fma', 'achieved': achieved_tflops, 'peak': fp64_peak, 'unit': 'TFLOP/s',
                 'frac': (achieved_tflops / fp64_peak) if fp64_peak else None,
                 'peak_source': 'measured in this run by spcies_b200/csrc/microbench.cu (register-only DMMA.8x8x4 / DFMA, full chip, '
                                'whichever is higher); MEASURED_PEAKS.json has no FP64 figure',
-                'kernel': 'spcies::fista::fista_mma_kernel (per step: %d launches = iteration-cap rounds; algorithmic FMA = SURVEY 8(d) '
-                          'count of the reference algorithm, not the padded 8x8x4 MMA slots)' % infos[-1]['launches'],
-                'kernel_ms': kernel_ms, 'traffic': ncu_traffic(infos[-1]['launches']),
+                'kernel': '%s (per step: %d launch(es); algorithmic FMA = SURVEY 8(d) count of the reference algorithm, not the '
+                          'padded 8x8x4 MMA slots)' % (KERNELS.get(spec.options.solver_key(), '?'), infos[-1]['launches']),
+                'kernel_ms': kernel_ms, 'traffic': ncu_traffic(infos[-1]['launches']) if args.config == 'C2' else None,
                 'traffic_source': 'dram__bytes_read.sum + dram__bytes_write.sum over the launches of one step, ncu --set full capture of '
                                   'this command (profiles/r1_fista_mma_ncu_summary.txt); algorithmic batch I/O is roofline.hbm',
                 'algorithmic_fma_per_launch': fma, 'sum_k_per_launch': sum_k,

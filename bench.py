@@ -360,7 +360,9 @@ def main():
     # engine issues DMMA.8x8x4; both instruction kinds share the pipe)
     fp64_peak = 2.0 * max(micro.get('fp64_tfma_per_s', 0.0), micro.get('fp64_dmma_tfma_per_s', 0.0)) if micro and 'fp64_tfma_per_s' in micro else None
     io_bytes = B * (8 * (2 * n + m + (1 if sol.has_r else 0)) + 8 * m + 8)
-    roofline = {'bound': 'fp64_fma', 'achieved': achieved_tflops, 'peak': fp64_peak, 'unit': 'TFLOP/s',
+    roofline = {'bound': 'tensor', 'bound_detail': 'FP64 tensor cores (mma.sync m8n8k4 = SASS DMMA.8x8x4; tcgen05 has no FP64 kind); DMMA '
+                                                   'shares the FP64 datapath with DFMA / DADD / DSETP, so this is the FP64 issue ceiling',
+                'achieved': achieved_tflops, 'peak': fp64_peak, 'unit': 'TFLOP/s',
                 'frac': (achieved_tflops / fp64_peak) if fp64_peak else None,
                 'peak_source': 'measured in this run by spcies_b200/csrc/microbench.cu (register-only DMMA.8x8x4 / DFMA, full chip, '
                                'whichever is higher); MEASURED_PEAKS.json has no FP64 figure',

@@ -466,6 +466,7 @@ struct Traits : PolicyTraits<Solver> {
         if constexpr (!HAS_MMA) return false;
         return mma_ok() && arith != SPCIES_CUDA_ARITH_EXACT && io.sol == nullptr && io.engine != SPCIES_CUDA_ENGINE_SCALAR;
     }
+    static bool uses_scratch(int arith, const BatchIO &io) { return !use_mma(arith, io); }
     static void engine_shape(int arith, const BatchIO &io, int &block, size_t &smem, int &ipb) {
         ipb = block;
         if (use_mma(arith, io)) {

@@ -789,6 +789,7 @@ struct Traits {
         return cudaErrorInvalidConfiguration;
     }
     static size_t scratch_bytes(int, int, bool) { return 0; }
+    static bool uses_scratch(int, const BatchIO &) { return false; }
     template <bool VARB>
     static cudaError_t launch_coop(int grid, cudaStream_t s, const BatchIO &io, const void *dc) {
         auto kern = fista_coop_kernel<VARB>;

@@ -217,7 +217,7 @@ template <class Traits> struct Runtime {
         long long want = (B + ipb - 1) / ipb;
         int grid = cl.grid > 0 ? cl.grid : c.sm_count;   // persistent: one CTA per SM
         if (want < grid) grid = (int)(want > 0 ? want : 1);
-        const size_t need_scratch = Traits::scratch_bytes(grid, block, varb);
+        const size_t need_scratch = Traits::uses_scratch(cl.arith, io) ? Traits::scratch_bytes(grid, block, varb) : 0;
         if (need_scratch > c.cap_scratch) {
             if (c.d_scratch) SPCIES_CK(cudaFree(c.d_scratch));
             c.d_scratch = nullptr;

@@ -126,6 +126,7 @@ template <class S> struct PolicyTraits {
     static int resume_block(bool varb) { return default_block(varb); }
     static void engine_shape(int, const BatchIO &, int &block, size_t &, int &ipb) { ipb = block; }
     static bool caps_engine(int, const BatchIO &) { return false; }
+    static bool uses_scratch(int, const BatchIO &) { return true; }   // the global per-instance state of the scalar kernels
     static constexpr int K_MAX = 0;
     static cudaError_t init_device_symbols() { return cudaSuccess; }
     static int default_block(bool varb) { return varb ? P::BLOCK_VARB : P::BLOCK_FIXED; }

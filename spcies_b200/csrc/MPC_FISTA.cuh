@@ -750,7 +750,7 @@ struct Traits {
         ipb = block;
         if (use_mma(arith, io)) {
             block = (io.phase != 2 && io.B >= MMA_BULK_MIN) ? MMA_BLOCK_BULK : MMA_BLOCK;
-            smem = MMA_BYTES;
+            smem = block == MMA_BLOCK_BULK ? MMA_BULK_SMEM : MMA_BYTES;
             ipb = block / 4;
         }
     }
@@ -804,12 +804,14 @@ struct Traits {
         if (io.engine == SPCIES_CUDA_ENGINE_MMA && !use_mma(arith, io)) return cudaErrorNotSupported;
         if constexpr (HAS_MMA) {
             if (use_mma(arith, io)) {
-                auto kern = block == MMA_BLOCK_BULK ? (varb ? fista_mma_kernel<true, MMA_BLOCK_BULK> : fista_mma_kernel<false, MMA_BLOCK_BULK>)
-                                                    : (varb ? fista_mma_kernel<true, MMA_BLOCK> : fista_mma_kernel<false, MMA_BLOCK>);
+                const bool bulk = block == MMA_BLOCK_BULK && MMA_BLOCK_BULK != MMA_BLOCK;
+                auto kern = bulk ? (varb ? fista_mma_kernel<true, MMA_BLOCK_BULK, BULK_SS> : fista_mma_kernel<false, MMA_BLOCK_BULK, BULK_SS>)
+                                 : (varb ? fista_mma_kernel<true, MMA_BLOCK, false> : fista_mma_kernel<false, MMA_BLOCK, false>);
                 if (block != MMA_BLOCK_BULK && block != MMA_BLOCK) return cudaErrorInvalidConfiguration;
-                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MMA_BYTES);
+                const size_t sm = bulk ? MMA_BULK_SMEM : MMA_BYTES;
+                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
                 if (e != cudaSuccess) return e;
-                kern<<<grid, block, MMA_BYTES, s>>>(io, (const unsigned char *)dc);
+                kern<<<grid, block, sm, s>>>(io, (const unsigned char *)dc);
                 return cudaGetLastError();
             }
         }
@@ -823,7 +825,7 @@ struct Traits {
     static cudaError_t attributes(int arith, bool varb, cudaFuncAttributes *a) {
         const bool ex = arith == SPCIES_CUDA_ARITH_EXACT;
         if constexpr (HAS_MMA) {
-            if (!ex) return varb ? cudaFuncGetAttributes(a, fista_mma_kernel<true, MMA_BLOCK>) : cudaFuncGetAttributes(a, fista_mma_kernel<false, MMA_BLOCK>);
+            if (!ex) return varb ? cudaFuncGetAttributes(a, fista_mma_kernel<true, MMA_BLOCK, false>) : cudaFuncGetAttributes(a, fista_mma_kernel<false, MMA_BLOCK, false>);
         }
         if (varb)
             return ex ? cudaFuncGetAttributes(a, fista_kernel<true, true, BLOCK1_VARB, USE_TMEM>)

@@ -50,6 +50,11 @@
 constexpr int MMA_BLOCK = SPCIES_FISTA_MMA_BLOCK;
 constexpr int MMA_BLOCK_BULK = SPCIES_FISTA_MMA_BLOCK_BULK;
 constexpr long long MMA_BULK_MIN = 16LL * 148 * (MMA_BLOCK_BULK / 4);   // batches of at least 16 waves use the bulk configuration
+#ifndef SPCIES_FISTA_MMA_BULK_SMEM
+#define SPCIES_FISTA_MMA_BULK_SMEM 0      // 1: the bulk configuration keeps lambda / mu' in shared memory (MERGE layout only).  Measured
+                                          // slower (tools/variants.py: 10.6 ms at 384 threads, 11.7 ms at 512, against 10.1 ms): the
+                                          // stage-batched products of pass A, not the iterates, hold the registers, so it still spills
+#endif
 constexpr bool HAS_MMA = SPCIES_FISTA_MMA != 0 && sizeof(real) == 8 && nm <= 8 && N >= 2 && N <= 12;
 constexpr int MMA_KTAB = k_max + 2;
 constexpr bool PRESCALE = SPCIES_FISTA_MMA_PRESCALE != 0;
@@ -108,6 +113,8 @@ struct alignas(16) MmaTables {
 constexpr size_t MMA_BYTES = (sizeof(MmaTables) + 15) / 16 * 16;
 constexpr size_t MMA_OFFSET = BLOB_BYTES;                 // position in the device constant blob
 constexpr size_t TOTAL_BLOB_BYTES = BLOB_BYTES + MMA_BYTES;
+constexpr bool BULK_SS = SPCIES_FISTA_MMA_BULK_SMEM != 0 && MERGE;
+constexpr size_t MMA_BULK_SMEM = MMA_BYTES + (BULK_SS ? (size_t)2 * N * MMA_BLOCK_BULK * sizeof(double2) : 0);
 
 static inline void fill_mma_tables(const spcies_consts &C, const FistaDerived &D, MmaTables &T) {
     memset(&T, 0, sizeof T);
@@ -210,8 +217,12 @@ __device__ __forceinline__ void mma_mv(double (&out)[2], const double2 M, const 
 }
 __device__ __forceinline__ double2 mma_mat(const double *M, int lane) { return reinterpret_cast<const double2 *>(M)[lane]; }
 
-template <bool VARB, int BLOCK>
+// SS (bulk configuration, MERGE layout only): lambda and mu' live in shared memory as [vector][stage][thread] double2 (one
+// conflict-free 128-bit access per lane) instead of registers; only y stays in registers, so that 4 warps per SM scheduler fit the
+// register file without spills (128 registers) and keep the FP64 pipe busy.
+template <bool VARB, int BLOCK, bool SS>
 __global__ void __launch_bounds__(BLOCK, 1) fista_mma_kernel(const BatchIO io, const unsigned char *__restrict__ g_blob) {
+    static_assert(!SS || MERGE, "shared-memory iterates are implemented for the MERGE layout");
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint64_t mbar;
@@ -272,7 +283,42 @@ __global__ void __launch_bounds__(BLOCK, 1) fista_mma_kernel(const BatchIO io, c
     long long inst = -1;
     int k = 0, grace_left = io.grace;
     bool live = false, drained = false, park_ok = io.park != nullptr;
-    double y[N][2], lam[N][2], w[N][2], q[2] = {0, 0}, qT[2] = {0, 0};
+    double y[N][2], lam[N][2], w[N][2], q[2] = {0, 0}, qT[2] = {0, 0};   // SS: lam / w are not used (the compiler drops them)
+    double2 *sst = reinterpret_cast<double2 *>(smem_raw + MMA_BYTES) + threadIdx.x;   // SS: lambda_l at [l], mu'_l at [N + l]
+    auto getL = [&](int l, double (&v)[2]) {
+        if constexpr (SS) {
+            const double2 t = sst[l * BLOCK];
+            v[0] = t.x;
+            v[1] = t.y;
+        } else {
+            v[0] = lam[l][0];
+            v[1] = lam[l][1];
+        }
+    };
+    auto setL = [&](int l, const double (&v)[2]) {
+        if constexpr (SS) sst[l * BLOCK] = make_double2(v[0], v[1]);
+        else {
+            lam[l][0] = v[0];
+            lam[l][1] = v[1];
+        }
+    };
+    auto getW = [&](int l, double (&v)[2]) {
+        if constexpr (SS) {
+            const double2 t = sst[(N + l) * BLOCK];
+            v[0] = t.x;
+            v[1] = t.y;
+        } else {
+            v[0] = w[l][0];
+            v[1] = w[l][1];
+        }
+    };
+    auto setW = [&](int l, const double (&v)[2]) {
+        if constexpr (SS) sst[(N + l) * BLOCK] = make_double2(v[0], v[1]);
+        else {
+            w[l][0] = v[0];
+            w[l][1] = v[1];
+        }
+    };
     double lo0[2] = {0, 0}, hi0[2] = {0, 0};   // "stage -1": lo = hi = x0 on the state components, the bounds of u_0 on the others
 #pragma unroll
     for (int l = 0; l < N; ++l)
@@ -318,6 +364,10 @@ __global__ void __launch_bounds__(BLOCK, 1) fista_mma_kernel(const BatchIO io, c
                             for (int i = 0; i < 2; ++i) {
                                 y[l][i] = xs[i] ? pk[(3 + l * n + xe[i]) * io.park_in_cap] : 0.0;
                                 lam[l][i] = xs[i] ? pk[(3 + N * n + l * n + xe[i]) * io.park_in_cap] : 0.0;
+                            if constexpr (SS) {
+#pragma unroll
+                                for (int l = 0; l < N; ++l) setL(l, lam[l]);
+                            }
                             }
                     } else {
                         k = -1;                                       // the warm-up pass brings it to 0
@@ -325,6 +375,10 @@ __global__ void __launch_bounds__(BLOCK, 1) fista_mma_kernel(const BatchIO io, c
                         for (int l = 0; l < N; ++l)
 #pragma unroll
                             for (int i = 0; i < 2; ++i) y[l][i] = lam[l][i] = 0.0;
+                        if constexpr (SS) {
+#pragma unroll
+                            for (int l = 0; l < N; ++l) setL(l, lam[l]);
+                        }
                     }
                     live = true;
                 }
@@ -392,12 +446,15 @@ __global__ void __launch_bounds__(BLOCK, 1) fista_mma_kernel(const BatchIO io, c
             double e[N][2];
 #pragma unroll
             for (int l = 0; l < N; ++l) dmma(e[l][0], e[l][1], r[l][0], T->FWa[l][lane].x, 0.0, 0.0);
-            dmma(w[0][0], w[0][1], r[0][1], T->FWb[0][lane], e[0][0], e[0][1]);
+            double mu[2];
+            dmma(mu[0], mu[1], r[0][1], T->FWb[0][lane], e[0][0], e[0][1]);
+            setW(0, mu);
 #pragma unroll
             for (int l = 1; l < N; ++l) {
                 double f0, f1;
-                dmma(f0, f1, w[l - 1][0], T->FWa[l][lane].y, e[l][0], e[l][1]);
-                dmma(w[l][0], w[l][1], lo2 ? r[l][1] : w[l - 1][1], T->FWb[l][lane], f0, f1);
+                dmma(f0, f1, mu[0], T->FWa[l][lane].y, e[l][0], e[l][1]);
+                dmma(mu[0], mu[1], lo2 ? r[l][1] : mu[1], T->FWb[l][lane], f0, f1);
+                setW(l, mu);
             }
         } else {
             double sl[N][2];
@@ -451,26 +508,34 @@ __global__ void __launch_bounds__(BLOCK, 1) fista_mma_kernel(const BatchIO io, c
         const double beta = T->beta[(live && k > 0) ? k : 0];
         auto update = [&](int l, const double (&d)[2]) {
 #pragma unroll
+            double l1[2], ln[2];
+            getL(l, l1);
+#pragma unroll
             for (int i = 0; i < 2; ++i) {
-                const double ln = y[l][i] + d[i];                   // lambda_l = y_l + d_lambda_l
-                y[l][i] = fma(beta, ln - lam[l][i], ln);            // y_l = lambda_l + beta (lambda_l - lambda1_l)
-                lam[l][i] = ln;
+                ln[i] = y[l][i] + d[i];                             // lambda_l = y_l + d_lambda_l
+                y[l][i] = fma(beta, ln[i] - l1[i], ln[i]);          // y_l = lambda_l + beta (lambda_l - lambda1_l)
             }
+            setL(l, ln);
         };
         if constexpr (MERGE) {
             // d_lambda_l = Uinv_l mu_l - G_l d_lambda_{l+1}:  g_l = Uinv mu (full k-step, issued one stage ahead),
             // h = g_l - G d_{l+1} (full k-step), d_l = h + [Uinv | -G] (mu_l, d_{l+1}) (the shared k-step)
-            double d[2], g0, g1, gn0 = 0.0, gn1 = 0.0;
-            dmma(g0, g1, w[N - 1][0], T->BWa[N - 1][lane].x, 0.0, 0.0);
-            if (N > 1) dmma(gn0, gn1, w[N - 2][0], T->BWa[N - 2][lane].x, 0.0, 0.0);
-            dmma(d[0], d[1], w[N - 1][1], T->BWb[N - 1][lane], g0, g1);
+            double d[2], g0, g1, gn0 = 0.0, gn1 = 0.0, wl[2], wp[2];   // mu'_l, mu'_{l-1}
+            getW(N - 1, wl);
+            getW(N - 2, wp);
+            dmma(g0, g1, wl[0], T->BWa[N - 1][lane].x, 0.0, 0.0);
+            dmma(gn0, gn1, wp[0], T->BWa[N - 2][lane].x, 0.0, 0.0);
+            dmma(d[0], d[1], wl[1], T->BWb[N - 1][lane], g0, g1);
             update(N - 1, d);
 #pragma unroll
             for (int l = N - 2; l >= 0; --l) {
                 double h0, h1;
+                wl[0] = wp[0];
+                wl[1] = wp[1];
+                if (l > 0) getW(l - 1, wp);
                 dmma(h0, h1, d[0], T->BWa[l][lane].y, gn0, gn1);
-                if (l > 0) dmma(gn0, gn1, w[l - 1][0], T->BWa[l - 1][lane].x, 0.0, 0.0);
-                dmma(d[0], d[1], lo2 ? w[l][1] : d[1], T->BWb[l][lane], h0, h1);
+                if (l > 0) dmma(gn0, gn1, wp[0], T->BWa[l - 1][lane].x, 0.0, 0.0);
+                dmma(d[0], d[1], lo2 ? wl[1] : d[1], T->BWb[l][lane], h0, h1);
                 update(l, d);
             }
         } else {
@@ -508,13 +573,16 @@ __global__ void __launch_bounds__(BLOCK, 1) fista_mma_kernel(const BatchIO io, c
                     pk[2 * io.park_cap] = 0.0;                      // t: implied by k in this engine
                 }
 #pragma unroll
-                for (int l = 0; l < N; ++l)
+                for (int l = 0; l < N; ++l) {
+                    double lv[2];
+                    getL(l, lv);
 #pragma unroll
                     for (int i = 0; i < 2; ++i)
                         if (xs[i]) {
                             pk[(3 + l * n + xe[i]) * io.park_cap] = y[l][i];
-                            pk[(3 + N * n + l * n + xe[i]) * io.park_cap] = lam[l][i];
+                            pk[(3 + N * n + l * n + xe[i]) * io.park_cap] = lv[i];
                         }
+                }
                 live = false;
             }
         }

@@ -16,10 +16,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 VARIANTS = {
-    'scalar_tmem8w': ['-DSPCIES_FISTA_MMA=0'],
-    'mma_mixed': [],
-    'mma256only': ['-DSPCIES_FISTA_MMA_BLOCK_BULK=256'],
-    'mma_bulk320': ['-DSPCIES_FISTA_MMA_BLOCK_BULK=320'],
+    'default': [],
+    'bulk384_ss': ['-DSPCIES_FISTA_MMA_BULK_SMEM=1'],
+    'bulk512_ss': ['-DSPCIES_FISTA_MMA_BLOCK_BULK=512', '-DSPCIES_FISTA_MMA_BULK_SMEM=1'],
+    'bulk256': ['-DSPCIES_FISTA_MMA_BLOCK_BULK=256'],
+    'nomerge': ['-DSPCIES_FISTA_MMA_MERGE=0'],
+    'scalar': ['-DSPCIES_FISTA_MMA=0'],
 }
 VARIANTS.update(json.loads(os.environ.get('SPCIES_VARIANTS', '{}')))
 LIST = os.path.join(ROOT, 'generated_solvers', 'variants.json')
@@ -75,8 +77,8 @@ def run(B):
                     two_phase_same_bits=bool(np.array_equal(u.view(np.uint64), u1.view(np.uint64)) and np.array_equal(k, k1)),
                     parked=info['parked'])
         out[name] = dict(exact=exact, exact_two_phase=exact2, parked_small=parked_small, fast=fast, runs={})
-        runs = [(1, 0, ()), (3, 0, (96, 320)), (3, 0, (128,)), (3, 0, (64, 256)), (3, 0, (160, 480))]
-        if 'scalar' in name:
+        runs = [(1, 0, ()), (3, 0, (96, 320)), (3, 0, (128,))]
+        if name == 'scalar':
             runs = [(1, 0, ()), (2, 32, ())]
         for mode, grace, caps in runs:
             ms = []

@@ -395,6 +395,86 @@ __global__ void __launch_bounds__(BLOCK, 1) fista_mma_kernel(const BatchIO io, c
         // interleaved with the independent w_{l-1} = Uinv_{l-1} mu_{l-1} products.
         // Components that a vector does not use hold finite don't-care values where the consuming matrix has zero columns
         // (the input part of z_l inside r_l), exact zeros elsewhere; the exit test only looks at state components.
+        bool over = false;
+        double u0v[2];
+        if constexpr (SS) {
+            // Bulk configuration: the same products, but the stages are taken in groups of G so that the live set of a pass is
+            // G + 1 z vectors, G residuals and G partial products instead of N of each (4 warps per scheduler share the register
+            // file; with that many warps the latency of a group's dependent MMAs is covered by the other warps).
+            constexpr int G = 5;
+            double zprev[2], mu[2] = {0.0, 0.0};
+            {   // "stage -1": (x0, u_0)
+                double a[2];
+                mma_mv(a, nabt, y[0], q[0], q[1]);
+#pragma unroll
+                for (int i = 0; i < 2; ++i) zprev[i] = u0v[i] = clip(a[i], lo0[i], hi0[i]);
+            }
+#pragma unroll
+            for (int g0 = 0; g0 < N; g0 += G) {
+                double zg[G + 1][2], rg[G][2], eg[G][2];
+                zg[0][0] = zprev[0];
+                zg[0][1] = zprev[1];
+#pragma unroll
+                for (int j = 0; j < G; ++j)
+                    if (g0 + j < N - 1) dmma(eg[j][0], eg[j][1], y[g0 + j + 1][0], nabt.x, q[0], q[1]);
+#pragma unroll
+                for (int j = 0; j < G; ++j)
+                    if (g0 + j < N - 1) dmma(zg[j + 1][0], zg[j + 1][1], y[g0 + j + 1][1], nabt.y, eg[j][0], eg[j][1]);
+#pragma unroll
+                for (int j = 0; j < G; ++j) {
+                    const int l = g0 + j;
+                    if (l < N - 1) {
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            double lo, hi;
+                            bnd(l + 1, i, lo, hi);
+                            zg[j + 1][i] = clip(fma(qriy[i], y[l][i], zg[j + 1][i]), lo, hi);          // z_l       :494-519
+                        }
+                    } else if (l == N - 1) {
+#if SPCIES_TERMINAL
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            double lo, hi;
+                            bnd(N, i, lo, hi);
+                            zg[j + 1][i] = clip(fma(ti[i], y[N - 1][i], qT[i]), lo, hi);              // z_N       :522-537
+                        }
+#else
+                        zg[j + 1][0] = qT[0];
+                        zg[j + 1][1] = qT[1];
+#endif
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < G; ++j)
+                    if (g0 + j < N) dmma(eg[j][0], eg[j][1], zg[j][0], nab.x, zg[j + 1][0], zg[j + 1][1]);
+#pragma unroll
+                for (int j = 0; j < G; ++j)
+                    if (g0 + j < N) dmma(rg[j][0], rg[j][1], zg[j][1], nab.y, eg[j][0], eg[j][1]);          // r_l       :549-572
+#pragma unroll
+                for (int j = 0; j < G; ++j)
+                    if (g0 + j < N) over = over || (fabs(rg[j][0]) > tolv[0]) || (fabs(rg[j][1]) > tolv[1]);
+#pragma unroll
+                for (int j = 0; j < G; ++j)
+                    if (g0 + j < N) dmma(eg[j][0], eg[j][1], rg[j][0], T->FWa[g0 + j][lane].x, 0.0, 0.0);
+#pragma unroll
+                for (int j = 0; j < G; ++j) {
+                    const int l = g0 + j;
+                    if (l < N) {
+                        if (l == 0) {
+                            dmma(mu[0], mu[1], rg[j][1], T->FWb[0][lane], eg[j][0], eg[j][1]);
+                        } else {
+                            double f0, f1;
+                            dmma(f0, f1, mu[0], T->FWa[l][lane].y, eg[j][0], eg[j][1]);
+                            dmma(mu[0], mu[1], lo2 ? rg[j][1] : mu[1], T->FWb[l][lane], f0, f1);
+                        }
+                        setW(l, mu);
+                    }
+                }
+                constexpr int LAST = G;
+                zprev[0] = zg[LAST][0];
+                zprev[1] = zg[LAST][1];
+            }
+        } else {
         double zz[N + 1][2];   // zz[0] = (x0, u_0), zz[l+1] = z_l (l < N-1), zz[N] = z_N (lax) | xr (equ)
         {
             // QRi o (q - [A B]' y_s) for every stage s                                      :474-519
@@ -407,7 +487,8 @@ __global__ void __launch_bounds__(BLOCK, 1) fista_mma_kernel(const BatchIO io, c
 #pragma unroll
         for (int i = 0; i < 2; ++i)                                                        // u_0; lo0 = hi0 = x0 on the state part
             zz[0][i] = clip(PRESCALE ? zz[0][i] : zz[0][i] * qri[i], lo0[i], hi0[i]);
-        const double u0v[2] = {zz[0][0], zz[0][1]};
+        u0v[0] = zz[0][0];
+        u0v[1] = zz[0][1];
 #pragma unroll
         for (int l = 0; l < N - 1; ++l)
 #pragma unroll
@@ -436,7 +517,6 @@ __global__ void __launch_bounds__(BLOCK, 1) fista_mma_kernel(const BatchIO io, c
 #pragma unroll
             for (int l = 0; l < N; ++l) dmma(r[l][0], r[l][1], zz[l][1], nab.y, e[l][0], e[l][1]);
         }
-        bool over = false;
 #pragma unroll
         for (int l = 0; l < N; ++l) over = over || (fabs(r[l][0]) > tolv[0]) || (fabs(r[l][1]) > tolv[1]);
         // forward step: mu_l = Linv_l r_l - F_l mu_{l-1}   [plain layout: and w_l = Uinv_l mu_l, stored in w]
@@ -483,6 +563,7 @@ __global__ void __launch_bounds__(BLOCK, 1) fista_mma_kernel(const BatchIO io, c
             mma_mv(w[N - 1], mma_mat(T->Uinv[N - 1], lane), mu, 0.0, 0.0);
         }
 
+        }
         // ================= exit condition                                            :337-361 =================
         if (live) k += 1;
         const bool gover = (__ballot_sync(FULL, over) & gmask) != 0u;

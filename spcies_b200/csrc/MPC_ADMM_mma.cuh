@@ -29,7 +29,7 @@
 #define SPCIES_ADMM_MMA_BLOCK 256
 #endif
 
-#if defined(SCALAR_RHO) && !defined(VAR_BOUNDS) && SPCIES_TERMINAL == 0
+#if defined(SCALAR_RHO) && !defined(VAR_BOUNDS) && (SPCIES_TERMINAL == 0 || SPCIES_TERMINAL == 1)
 #define SPCIES_ADMM_MMA_ELIGIBLE 1
 #else
 #define SPCIES_ADMM_MMA_ELIGIBLE 0
@@ -38,7 +38,8 @@
 constexpr int MMA_BLOCK = SPCIES_ADMM_MMA_BLOCK;
 constexpr int MMA_IPB = MMA_BLOCK / 4;
 constexpr bool MMA_SHAPE_OK = n >= 5 && n <= 6 && nm <= 8 && N >= 3;
-constexpr size_t MMA_STATE_PER_WARP = (size_t)2 * N * 32 * sizeof(double2);   // v and lambda blocks
+constexpr int MMA_NBLK = N + (HAS_TN ? 1 : 0);   // blocks of v / lambda: u_0, stages 0..N-2 [, the terminal state of laxMPC]
+constexpr size_t MMA_STATE_PER_WARP = (size_t)2 * MMA_NBLK * 32 * sizeof(double2);
 
 #if SPCIES_ADMM_MMA_ELIGIBLE
 struct alignas(16) MmaTables {
@@ -48,6 +49,8 @@ struct alignas(16) MmaTables {
     double2 FWa[N][32], BWa[N][32];
     double FWb[N][32], BWb[N][32];
     double Hi[8];             // inverse of the (diagonal) Hessian + rho, by column of z; the same for every block (checked on the host)
+    double HiN[64], NHiN[64]; // laxMPC: the dense terminal block Hi_N and its negative, [output column][input column] (x columns)
+    double Tm[8][8];          // laxMPC: T by component (qT = T xr, computed per instance at refill)
     double Qs[8];             // q = Qs o [xr; ur]   (Q, R stored negated)
     double LB[8], UB[8];
     int xat[8], uat[8];
@@ -84,6 +87,16 @@ static inline bool fill_mma_tables(const spcies_consts &C, MmaTables &T) {
             if (L::x_at(oc) >= 0 && L::z_at(ic) >= 0) T.NAB[oc * 8 + ic] = -(double)C.AB[L::x_at(oc)][L::z_at(ic)];
             if (L::z_at(oc) >= 0 && L::x_at(ic) >= 0) T.ABt[oc * 8 + ic] = (double)C.AB[L::x_at(ic)][L::z_at(oc)];
         }
+#if SPCIES_TERMINAL == 1
+    for (int oc = 0; oc < 8; ++oc)
+        for (int ic = 0; ic < 8; ++ic)
+            if (L::x_at(oc) >= 0 && L::x_at(ic) >= 0) {
+                T.HiN[oc * 8 + ic] = (double)C.Hi_N[L::x_at(oc)][L::x_at(ic)];
+                T.NHiN[oc * 8 + ic] = -(double)C.Hi_N[L::x_at(oc)][L::x_at(ic)];
+            }
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) T.Tm[i][j] = (double)C.T[i][j];
+#endif
     typedef double Blk[n][n];
     Blk *Linv = new Blk[4 * N], *F = Linv + N, *Uinv = F + N, *G = Uinv + N;
     mma::block_inverses<N, n>(C, Linv, F, Uinv, G);
@@ -133,7 +146,11 @@ __global__ void __launch_bounds__(MMA_BLOCK, 1) admm_mma_kernel(const BatchIO io
     long long inst = -1;
     int k = 0;
     bool live = false, drained = false;
-    double q[2] = {0, 0}, nx0[2] = {0, 0}, nxr[2] = {0, 0};
+    double q[2] = {0, 0}, nx0[2] = {0, 0}, nxr[2] = {0, 0};   // laxMPC: nxr holds qT = T xr instead of -xr
+#if SPCIES_TERMINAL == 1
+    const double2 hin = reinterpret_cast<const double2 *>(T->HiN)[lane], nhin = reinterpret_cast<const double2 *>(T->NHiN)[lane];
+    const double tolxs[2] = {xs[0] ? (double)tol : 1e300, xs[1] ? (double)tol : 1e300};
+#endif
 
     for (;;) {
         // ---- refill: a lane group without an instance pulls the next one          code_equMPC_ADMM_C.c:268-283
@@ -154,7 +171,14 @@ __global__ void __launch_bounds__(MMA_BLOCK, 1) admm_mma_kernel(const BatchIO io
                         const double ur_ = us[i] ? io.ur[inst * m + ue[i]] : 0.0;
                         q[i] = qs[i] * (xs[i] ? xr_ : ur_);
                         nx0[i] = xs[i] ? -io.x0[inst * n + xe[i]] : 0.0;
+#if SPCIES_TERMINAL == 1
+                        double qt = 0.0;                                   // qT = T xr (T dense, negated)   code_laxMPC_ADMM_C.c:292-295
+                        if (xs[i])
+                            for (int j = 0; j < n; ++j) qt = fma(T->Tm[xe[i]][j], io.xr[inst * n + j], qt);
+                        nxr[i] = qt;
+#else
                         nxr[i] = -xr_;
+#endif
                         if (VARB) {
                             const int ze = xs[i] ? xe[i] : n + ue[i];
                             lb[i] = (xs[i] || us[i]) ? io.LB[inst * nm + ze] : -1e300;
@@ -162,7 +186,7 @@ __global__ void __launch_bounds__(MMA_BLOCK, 1) admm_mma_kernel(const BatchIO io
                         }
                     }
 #pragma unroll 4
-                    for (int e = 0; e < 2 * N; ++e) st[e * 32] = make_double2(0.0, 0.0);
+                    for (int e = 0; e < 2 * MMA_NBLK; ++e) st[e * 32] = make_double2(0.0, 0.0);
                     k = 0;
                     live = true;
                 }
@@ -173,6 +197,9 @@ __global__ void __launch_bounds__(MMA_BLOCK, 1) admm_mma_kernel(const BatchIO io
 
         // ================= pass A: q_hat -> s -> r.h.s. -> forward recurrence =================
         double mup[N][2];   // mu'_b (with the second copies of x_4.. in register 1 of lanes 2,3)
+#if SPCIES_TERMINAL == 1
+        double zNh[2] = {0.0, 0.0};   // z_N_hat = qT + lambda_N - rho v_N
+#endif
         {
             double sp[2];   // s_{b}
             {
@@ -196,8 +223,16 @@ __global__ void __launch_bounds__(MMA_BLOCK, 1) admm_mma_kernel(const BatchIO io
                         s[j + 1][0] = hi[0] * fma(-rho_, v.x, q[0] + la.x);
                         s[j + 1][1] = hi[1] * fma(-rho_, v.y, q[1] + la.y);
                     } else {
+#if SPCIES_TERMINAL == 1
+                        // laxMPC: s_N = Hi_N (qT + lambda_N - rho v_N)                      code_laxMPC_ADMM_C.c:373-381
+                        const double2 v = LDV(N), la = LDL(N);
+                        zNh[0] = xs[0] ? fma(-rho_, v.x, nxr[0] + la.x) : 0.0;
+                        zNh[1] = xs[1] ? fma(-rho_, v.y, nxr[1] + la.y) : 0.0;
+                        mma::mv(s[j + 1], hin, zNh, 0.0, 0.0);
+#else
                         s[j + 1][0] = nxr[0];           // :351-353
                         s[j + 1][1] = nxr[1];
+#endif
                     }
                 }
 #pragma unroll
@@ -235,6 +270,23 @@ __global__ void __launch_bounds__(MMA_BLOCK, 1) admm_mma_kernel(const BatchIO io
             dmma(g0, g1, mup[N - 1][0], T->BWa[N - 1][lane].x, 0.0, 0.0);
             dmma(mu[0], mu[1], mup[N - 1][1], T->BWb[N - 1][lane], g0, g1);
         }
+#if SPCIES_TERMINAL == 1
+        {   // terminal block: z_N = -Hi_N (z_N_hat - mu_{N-1}), v_N, lambda_N           code_laxMPC_ADMM_C.c:476-485, :523-538, :561-569
+            const double aux[2] = {fma(-maskx[0], mu[0], zNh[0]), fma(-maskx[1], mu[1], zNh[1])};
+            double zn[2];
+            mma::mv(zn, nhin, aux, 0.0, 0.0);
+            const double2 v = LDV(N), la = LDL(N);
+            double2 vn, ln;
+            vn.x = xs[0] ? clip(fma(rhoi_, la.x, zn[0]), lb[0], ub[0]) : 0.0;
+            vn.y = xs[1] ? clip(fma(rhoi_, la.y, zn[1]), lb[1], ub[1]) : 0.0;
+            const double d0 = zn[0] - vn.x, d1 = zn[1] - vn.y;
+            over = over || (fabs(v.x - vn.x) > tolxs[0]) || (fabs(d0) > tolxs[0]) || (fabs(v.y - vn.y) > tolxs[1]) || (fabs(d1) > tolxs[1]);
+            ln.x = xs[0] ? fma(rho_, d0, la.x) : 0.0;
+            ln.y = xs[1] ? fma(rho_, d1, la.y) : 0.0;
+            st[(2 * N) * 32] = vn;
+            st[(2 * N + 1) * 32] = ln;
+        }
+#endif
         double u0v[2] = {0, 0};
 #pragma unroll
         for (int b = N - 1; b >= 0; --b) {

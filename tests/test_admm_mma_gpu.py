@@ -9,7 +9,7 @@ from spcies_b200 import prebuilt, sysmodel
 from spcies_b200.solver import ARITH_EXACT, ARITH_FAST, ENGINE_MMA, ENGINE_SCALAR, SpciesCudaError
 
 pytestmark = pytest.mark.gpu
-ADMM = ['T_equMPC_ADMM', 'C3_equMPC_ADMM']
+ADMM = ['T_equMPC_ADMM', 'C3_equMPC_ADMM', 'T_laxMPC_ADMM']      # equMPC and laxMPC (terminal block) run on the engine
 
 
 def _ref(name):
@@ -59,10 +59,16 @@ def test_admm_mma_ragged_batches():
             _gate(spec, u, k, e, ur_, kr, er)
 
 
-def test_admm_mma_per_instance_bounds():
+@pytest.mark.parametrize('name', ['T_equMPC_ADMM', 'T_laxMPC_ADMM'])
+def test_admm_mma_per_instance_bounds(name):
     """opts.LB / UB: bounds equal to the generated constants reproduce the constant-bounds call bit for bit; random
-    per-instance bounds agree with the scalar engine (itself pinned against regenerated references for FISTA) within the gate."""
-    sol, spec, cfg = prebuilt.get('T_equMPC_ADMM')
+    per-instance bounds agree with the EXACT scalar kernel (bit-identical to the reference for constant bounds) within the
+    gate.  laxMPC: the terminal block takes the state part of the per-instance bounds."""
+    _per_instance_bounds(name)
+
+
+def _per_instance_bounds(name):
+    sol, spec, cfg = prebuilt.get(name)
     B = 1200
     batch = sysmodel.synthetic_batch(cfg['sys'], B, seed=53)
     LB = np.tile(np.concatenate([cfg['sys']['LBx'], cfg['sys']['LBu']]), (B, 1))
@@ -80,10 +86,10 @@ def test_admm_mma_per_instance_bounds():
 
 
 def test_admm_mma_engine_is_refused_where_it_cannot_run():
-    batchcfg = prebuilt.get('T_laxMPC_ADMM')
+    batchcfg = prebuilt.get('T_ellipMPC_ADMM')
     sol, spec, cfg = batchcfg
     batch = sysmodel.synthetic_batch(cfg['sys'], 64, seed=54)
-    with pytest.raises(SpciesCudaError):                                  # terminal block: scalar kernel only
+    with pytest.raises(SpciesCudaError):                                  # terminal ellipsoid: scalar kernel only
         sol.solve_batch(batch['x0'], batch['xr'], batch['ur'], engine=ENGINE_MMA)
     sol.solve_batch(batch['x0'], batch['xr'], batch['ur'])
     sol, spec, cfg = prebuilt.get('T_equMPC_ADMM')

@@ -346,6 +346,45 @@ def main():
                         'all_cores': {'value': rate_all, 'cores': cores, 'seconds': dt_all},
                         'mean_k': float(kr.mean())}
 
+    # ---- single-solve latency through the unchanged single-instance symbol (BASELINE.json metric, second half):
+    #      p50 over repeated calls at the reference test point, next to the reference C solver called the same way (ctypes)
+    single = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and 'status' in cfg:
+        stt = cfg['status']
+        rr = cfg['param'].get('r', None) if sol.has_r else None
+        def p50_us(fn, reps):
+            for _ in range(20):
+                fn()
+            ts = []
+            for _ in range(reps):
+                t0 = time.perf_counter()
+                fn()
+                ts.append(time.perf_counter() - t0)
+            return float(np.median(ts) * 1e6), float(np.percentile(ts, 99) * 1e6)
+        g50, g99 = p50_us(lambda: sol.solve(stt['x'], stt['xr'], stt['ur'], rr), 1000)
+        ks = sol.solve(stt['x'], stt['xr'], stt['ur'], rr)[1]
+        # the reference C solver at the same point: mean over a single-thread batch of identical instances (no Python per call)
+        from oracle import refs as _refs
+        ref1 = _refs.get(save_name)[0]
+        nrep = 2000 if 'HMPC' not in save_name else 20
+        rep = lambda v: np.repeat(np.asarray(v, dtype=np.float64)[None], nrep, axis=0)
+        t0 = time.perf_counter()
+        ref1.solve_batch(rep(stt['x']), rep(stt['xr']), rep(stt['ur']), threads=1, **({'r': np.full(nrep, rr)} if sol.has_r else {}))
+        c_us = (time.perf_counter() - t0) / nrep * 1e6
+        # the same symbol called from plain C (harness/main_batch.c, the reference's examples/cl_in_C pattern): no ctypes overhead
+        c_p50 = None
+        exe = os.path.join(ROOT, 'harness', 'main_batch')
+        if args.config == 'C2' and os.path.exists(exe):
+            try:
+                out = subprocess.run([exe, '64', '0'], capture_output=True, text=True, timeout=120).stdout
+                c_p50 = float(out.split('p50 latency =')[1].split('us')[0])
+            except Exception:
+                c_p50 = None
+        single = {'p50_us': c_p50 if c_p50 is not None else g50, 'p50_us_ctypes': g50, 'p99_us_ctypes': g99, 'k': int(ks),
+                  'cpu_reference_us': c_us,
+                  'how': 'single-instance symbol (batch of one: H2D, kernel, D2H): p50 of 200 calls from plain C (harness/main_batch) when '
+                         'available, p50 / p99 of 1000 calls through ctypes; reference C solver: mean of %d identical solves, one thread' % nrep}
+
     sum_k_all = sum_over_ranks(sum_k)
     if rank != 0:
         if world > 1:
@@ -384,7 +423,7 @@ def main():
                     'h2d_ms': float(np.mean([x['h2d_ms'] for x in hinfos])),
                     'd2h_ms': float(np.mean([x['d2h_ms'] for x in hinfos]))},
             'gpu_launches': int(sum(x['launches'] for x in infos)) * world,
-            'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu_baseline, 'parity': parity,
+            'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu_baseline, 'parity': parity, 'single_solve': single,
             'mean_k': sum_k_all / (world * B), 'n_not_converged_per_batch': n_nc,
             'kernel': {'block_threads': infos[-1]['block_threads'], 'grid_blocks': infos[-1]['grid_blocks'],
                        'smem_bytes': infos[-1]['smem_bytes'], 'regs_per_thread': infos[-1]['regs_per_thread'],

@@ -53,6 +53,8 @@ struct DeviceCtx {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;          // host->device input chunks, overlapped with the solver kernel
     unsigned long long *h_ready = nullptr;       // pinned: watermark values copied to d_queue[8] after every chunk
+    double *h_stage = nullptr;                   // pinned, device-mapped staging of the small-batch path (zero-copy in / out)
+    double *d_stage = nullptr;                   // its device address
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     void *d_consts = nullptr;
     unsigned long long *d_queue = nullptr;
@@ -160,6 +162,7 @@ template <class Traits> struct Runtime {
             cudaStreamDestroy(c.stream);
             cudaStreamDestroy(c.copy_stream);
             cudaFreeHost(c.h_ready);
+            if (c.h_stage) cudaFreeHost(c.h_stage);
             c = DeviceCtx();
         }
     }
@@ -186,6 +189,78 @@ template <class Traits> struct Runtime {
         long long parked = 0;
     };
 
+    // Small host-buffer batches (the reference's single-instance call is a batch of one): latency is API calls, not bytes.
+    // Inputs are memcpy'd into a pinned, device-mapped staging block that the kernel reads directly, results come back the same
+    // way, the statistics are summed on the host: one memset, one launch, two event records and one synchronisation instead of
+    // seven copies.  Same kernels, same results.
+    static constexpr long long SMALL_B = 64;
+    static constexpr size_t stage_doubles() { return (size_t)SMALL_B * (2 * Traits::NN + 2 * Traits::MM + 1 + 2 * Traits::NMM + 1); }
+    int run_small(DeviceCtx &c, const Call &cl, Result &res) {
+        const long long B = cl.B;
+        const bool varb = cl.LB != nullptr && cl.UB != nullptr;
+        if (!c.h_stage) {
+            SPCIES_CK(cudaHostAlloc((void **)&c.h_stage, stage_doubles() * sizeof(double), cudaHostAllocMapped));
+            SPCIES_CK(cudaHostGetDevicePointer((void **)&c.d_stage, c.h_stage, 0));
+        }
+        // layout (doubles): x0 | xr | ur | r | LB | UB | u | (k, e as ints)
+        double *h = c.h_stage, *d = c.d_stage;
+        const size_t o_x0 = 0, o_xr = o_x0 + SMALL_B * Traits::NN, o_ur = o_xr + SMALL_B * Traits::NN, o_r = o_ur + SMALL_B * Traits::MM,
+                     o_lb = o_r + SMALL_B, o_ub = o_lb + SMALL_B * Traits::NMM, o_u = o_ub + SMALL_B * Traits::NMM,
+                     o_ke = o_u + SMALL_B * Traits::MM;
+        memcpy(h + o_x0, cl.x0, (size_t)B * Traits::NN * 8);
+        memcpy(h + o_xr, cl.xr, (size_t)B * Traits::NN * 8);
+        memcpy(h + o_ur, cl.ur, (size_t)B * Traits::MM * 8);
+        if (Traits::HAS_R) memcpy(h + o_r, cl.r, (size_t)B * 8);
+        if (varb) {
+            memcpy(h + o_lb, cl.LB, (size_t)B * Traits::NMM * 8);
+            memcpy(h + o_ub, cl.UB, (size_t)B * Traits::NMM * 8);
+        }
+        BatchIO io;
+        memset(&io, 0, sizeof io);
+        io.B = B;
+        io.queue = c.d_queue;
+        io.x0 = d + o_x0; io.xr = d + o_xr; io.ur = d + o_ur; io.r = d + o_r;
+        io.LB = varb ? d + o_lb : nullptr; io.UB = varb ? d + o_ub : nullptr;
+        io.u = d + o_u;
+        io.k = reinterpret_cast<int *>(d + o_ke);
+        io.e = io.k + SMALL_B;
+        io.engine = cl.engine;
+        int block = cl.block > 0 ? cl.block : Traits::default_block(varb), ipb = 0;
+        size_t smem = Traits::smem_bytes(block, varb);
+        Traits::engine_shape(cl.arith, io, block, smem, ipb);
+        int grid = (int)((B + ipb - 1) / ipb);
+        if (cl.grid > 0 && cl.grid < grid) grid = cl.grid;
+        if (grid > c.sm_count) grid = c.sm_count;
+        const size_t need_scratch = Traits::uses_scratch(cl.arith, io) ? Traits::scratch_bytes(grid, block, varb) : 0;
+        if (need_scratch > c.cap_scratch) {
+            if (c.d_scratch) SPCIES_CK(cudaFree(c.d_scratch));
+            c.d_scratch = nullptr;
+            SPCIES_CK(cudaMalloc(&c.d_scratch, need_scratch));
+            c.cap_scratch = need_scratch;
+        }
+        cudaStream_t s = c.stream;
+        SPCIES_CK(cudaMemsetAsync(c.d_queue, 0, QUEUE_WORDS * sizeof(unsigned long long), s));
+        SPCIES_CK(cudaEventRecord(c.ev[1], s));
+        SPCIES_CK(Traits::launch(cl.arith, varb, grid, block, smem, s, io, c.d_consts, c.d_scratch));
+        SPCIES_CK(cudaEventRecord(c.ev[2], s));
+        SPCIES_CK(cudaStreamSynchronize(s));
+        SPCIES_CK(cudaGetLastError());
+        memcpy(cl.u, h + o_u, (size_t)B * Traits::MM * 8);
+        const int *hk = reinterpret_cast<const int *>(h + o_ke), *he = hk + SMALL_B;
+        memcpy(cl.k, hk, (size_t)B * 4);
+        memcpy(cl.e, he, (size_t)B * 4);
+        float ms = 0;
+        SPCIES_CK(cudaEventElapsedTime(&ms, c.ev[1], c.ev[2]));
+        res.kernel_ms = ms;
+        for (long long i = 0; i < B; ++i) {
+            res.sum_k += hk[i];
+            res.n_nc += (he[i] < 0);
+        }
+        res.launches = 1;
+        res.block = block; res.grid = grid; res.smem = (int)smem;
+        return 0;
+    }
+
     // one device, one contiguous slice [off, off+B) of the caller's arrays
     int run_on_device(int dev, const Call &cl, Result &res) {
         DeviceCtx *pc;
@@ -195,6 +270,9 @@ template <class Traits> struct Runtime {
         const long long B = cl.B;
         const bool varb = cl.LB != nullptr && cl.UB != nullptr;
         if (varb && !Traits::HAS_VARB) return fail(SPCIES_CUDA_EUNSUPPORTED, "this solver was generated without per-instance bounds");
+        if (!cl.device_pointers && cl.sol == nullptr && B > 0 && B <= SMALL_B && cl.tail_mode != SPCIES_CUDA_TAIL_TWO_PHASE &&
+            cl.tail_mode != SPCIES_CUDA_TAIL_CAPS)
+            return run_small(c, cl, res);
         cudaStream_t s = (cl.device_pointers && cl.user_stream) ? cl.user_stream : c.stream;
         BatchIO io;
         memset(&io, 0, sizeof io);
@@ -436,8 +514,13 @@ template <class Traits> struct Runtime {
                 info->h2d_bytes = B * 8 * (2 * Traits::NN + Traits::MM + (Traits::HAS_R ? 1 : 0) + varb);
                 info->d2h_bytes = B * (8 * Traits::MM + 8) + (sol ? B * 8LL * Traits::SOL_DOUBLES : 0);
             }
-            cudaFuncAttributes fa;
-            if (Traits::attributes(o.arith, o.LB != nullptr, &fa) == cudaSuccess) info->regs_per_thread = fa.numRegs;
+            static int regs_cache[2][2] = {{0, 0}, {0, 0}};          // cudaFuncGetAttributes costs microseconds: once per variant
+            int &rcache = regs_cache[o.arith == SPCIES_CUDA_ARITH_EXACT ? 1 : 0][o.LB != nullptr ? 1 : 0];
+            if (rcache == 0) {
+                cudaFuncAttributes fa;
+                if (Traits::attributes(o.arith, o.LB != nullptr, &fa) == cudaSuccess) rcache = fa.numRegs;
+            }
+            info->regs_per_thread = rcache;
             info->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         }
         return 0;

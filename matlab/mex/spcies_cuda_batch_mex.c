@@ -48,6 +48,7 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
     opts.device = (int)opt_scalar(mopts, "device", 0);
     opts.n_devices = (int)opt_scalar(mopts, "n_devices", 1);
     opts.arith = opt_scalar(mopts, "exact", 0) != 0 ? SPCIES_CUDA_ARITH_EXACT : SPCIES_CUDA_ARITH_FAST;
+    opts.engine = (int)opt_scalar(mopts, "engine", SPCIES_CUDA_ENGINE_AUTO);   /* 0 auto | 1 scalar | 2 tensor-core (MMA) */
     const mxArray *LB = mopts ? mxGetField(mopts, 0, "LB") : NULL, *UB = mopts ? mxGetField(mopts, 0, "UB") : NULL;
     if (LB && UB) {
         if (mxGetM(LB) != nm_ || mxGetN(LB) != B || mxGetM(UB) != nm_ || mxGetN(UB) != B)

@@ -259,3 +259,22 @@ def test_plain_c_harness_runs():
     assert out.returncode == 0, out.stderr
     assert 'single solve: u = [0.800000 0.800000]' in out.stdout and 'e_flag = 1' in out.stdout
     assert 'closed loop step 2' in out.stdout
+
+
+@pytest.mark.parametrize('name,B', [('C3_equMPC_ADMM', 330_000), ('C4_ellipMPC_ADMM_soc', 300_000), ('C5b_MPCT_EADMM', 90_000),
+                                    ('C5a_HMPC_SADMM_split', 80_000)])
+def test_pipelined_host_copies_every_engine(name, B):
+    """Host-buffer calls large enough for the pipelined host->device copies (chunks arrive under the running kernel, the
+    instance queue waits on the watermark): every instance is solved exactly once and gets the bits of a call on the same
+    instances made in pieces below the pipelining threshold (results do not depend on which lane group solves an instance)."""
+    sol, spec, cfg = prebuilt.get(name)
+    batch, kw = _batch(sol, cfg, B, seed=91)
+    u, k, e, info = sol.solve_batch(batch['x0'], batch['xr'], batch['ur'], **kw)
+    assert info['sum_k'] == int(k.sum()) and info['n_not_converged'] == int((e == -1).sum())
+    assert set(np.unique(e)) <= {1, -1} and k.min() >= 1
+    rng = np.random.default_rng(7)
+    for lo in (0, B - 20_000, int(rng.integers(20_000, B - 40_000))):
+        sl = slice(lo, lo + 20_000)
+        kws = {kk: v[sl] for kk, v in kw.items()}
+        u2, k2, e2, _ = sol.solve_batch(batch['x0'][sl], batch['xr'][sl], batch['ur'][sl], **kws)
+        assert np.array_equal(u[sl].view(np.uint64), u2.view(np.uint64)) and np.array_equal(k[sl], k2) and np.array_equal(e[sl], e2)

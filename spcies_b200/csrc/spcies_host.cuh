@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -189,6 +190,14 @@ template <class Traits> struct Runtime {
         long long parked = 0;
     };
 
+    static bool direct_results() {
+        static const bool on = [] {
+            const char *v = getenv("SPCIES_CUDA_DIRECT_RESULTS");   // set to 0 to force the device->host copies
+            return v == nullptr || v[0] != '0';
+        }();
+        return on;
+    }
+
     // Small host-buffer batches (the reference's single-instance call is a batch of one): latency is API calls, not bytes.
     // Inputs are memcpy'd into a pinned, device-mapped staging block that the kernel reads directly, results come back the same
     // way, the statistics are summed on the host: one memset, one launch, two event records and one synchronisation instead of
@@ -274,6 +283,7 @@ template <class Traits> struct Runtime {
             cl.tail_mode != SPCIES_CUDA_TAIL_CAPS)
             return run_small(c, cl, res);
         cudaStream_t s = (cl.device_pointers && cl.user_stream) ? cl.user_stream : c.stream;
+        bool direct_out = false;
         BatchIO io;
         memset(&io, 0, sizeof io);
         io.B = B;
@@ -286,6 +296,18 @@ template <class Traits> struct Runtime {
             io.x0 = c.d_x0; io.xr = c.d_xr; io.ur = c.d_ur; io.r = c.d_r;
             io.LB = varb ? c.d_LB : nullptr; io.UB = varb ? c.d_UB : nullptr;
             io.u = c.d_u; io.k = c.d_k; io.e = c.d_e; io.sol = cl.sol ? c.d_sol : nullptr;
+            // results straight into the caller's arrays when those are pinned (device-mapped) host memory: 24 bytes per instance
+            // posted over PCIe under the running kernel instead of three device->host copies after it
+            if (direct_results()) {
+                cudaPointerAttributes au, ak, ae;
+                if (cudaPointerGetAttributes(&au, cl.u) == cudaSuccess && cudaPointerGetAttributes(&ak, cl.k) == cudaSuccess &&
+                    cudaPointerGetAttributes(&ae, cl.e) == cudaSuccess && au.type == cudaMemoryTypeHost && ak.type == cudaMemoryTypeHost &&
+                    ae.type == cudaMemoryTypeHost && au.devicePointer && ak.devicePointer && ae.devicePointer) {
+                    io.u = (double *)au.devicePointer; io.k = (int *)ak.devicePointer; io.e = (int *)ae.devicePointer;
+                    direct_out = true;
+                }
+                cudaGetLastError();   // cudaPointerGetAttributes on pageable memory may leave a sticky-free error code
+            }
         }
         io.engine = cl.engine;
         int block = cl.block > 0 ? cl.block : Traits::default_block(varb);
@@ -409,9 +431,11 @@ template <class Traits> struct Runtime {
         unsigned long long stats[QUEUE_WORDS] = {0};
         SPCIES_CK(cudaMemcpyAsync(stats, c.d_queue, sizeof stats, cudaMemcpyDeviceToHost, s));
         if (!cl.device_pointers) {
-            SPCIES_CK(cudaMemcpyAsync(cl.u, c.d_u, (size_t)B * Traits::MM * 8, cudaMemcpyDeviceToHost, s));
-            SPCIES_CK(cudaMemcpyAsync(cl.k, c.d_k, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
-            SPCIES_CK(cudaMemcpyAsync(cl.e, c.d_e, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+            if (!direct_out) {
+                SPCIES_CK(cudaMemcpyAsync(cl.u, c.d_u, (size_t)B * Traits::MM * 8, cudaMemcpyDeviceToHost, s));
+                SPCIES_CK(cudaMemcpyAsync(cl.k, c.d_k, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+                SPCIES_CK(cudaMemcpyAsync(cl.e, c.d_e, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+            }
             if (cl.sol)
                 SPCIES_CK(cudaMemcpyAsync(cl.sol, c.d_sol, (size_t)B * Traits::SOL_DOUBLES * 8, cudaMemcpyDeviceToHost, s));
         }

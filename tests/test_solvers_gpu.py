@@ -278,3 +278,19 @@ def test_pipelined_host_copies_every_engine(name, B):
         kws = {kk: v[sl] for kk, v in kw.items()}
         u2, k2, e2, _ = sol.solve_batch(batch['x0'][sl], batch['xr'][sl], batch['ur'][sl], **kws)
         assert np.array_equal(u[sl].view(np.uint64), u2.view(np.uint64)) and np.array_equal(k[sl], k2) and np.array_equal(e[sl], e2)
+
+
+def test_results_written_directly_into_pinned_host_arrays():
+    """When the caller's u_opt / k / e_flag arrays are pinned host memory the kernel writes them directly (no device->host
+    copies); the results are the bits of the call with pageable arrays."""
+    import torch
+    sol, spec, cfg = prebuilt.get('C2_laxMPC_FISTA')
+    for B in (200, 40_000):
+        batch = sysmodel.synthetic_batch(cfg['sys'], B, seed=92)
+        u0, k0, e0, _ = sol.solve_batch(batch['x0'], batch['xr'], batch['ur'])
+        hu = torch.full((B, sol.m), float('nan'), dtype=torch.float64).pin_memory()
+        hk = torch.full((B,), -7, dtype=torch.int32).pin_memory()
+        he = torch.full((B,), -7, dtype=torch.int32).pin_memory()
+        sol.solve_batch(batch['x0'], batch['xr'], batch['ur'], out=(hu.numpy(), hk.numpy(), he.numpy()))
+        assert np.array_equal(hu.numpy().view(np.uint64), u0.view(np.uint64))
+        assert np.array_equal(hk.numpy(), k0) and np.array_equal(he.numpy(), e0)

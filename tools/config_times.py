@@ -23,6 +23,11 @@ CONFIGS = {
     'C4_ellipMPC_ADMM_soc': (1 << 17, 512),
     'C5b_MPCT_EADMM': (1 << 17, 1024),
     'C5a_HMPC_SADMM_split': (1 << 15, 24),
+    # the remaining solvers of SURVEY 8(a), at the reference tests' settings (N = 10, tol 1e-7, k_max 5000)
+    'T_equMPC_FISTA': (1 << 17, 2048),
+    'T_laxMPC_ADMM': (1 << 17, 2048),
+    'T_ellipMPC_ADMM': (1 << 16, 2048),
+    'T_HMPC_ADMM_split': (1 << 15, 512),
 }
 
 

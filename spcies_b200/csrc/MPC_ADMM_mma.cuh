@@ -29,7 +29,7 @@
 #define SPCIES_ADMM_MMA_BLOCK 256
 #endif
 
-#if defined(SCALAR_RHO) && !defined(VAR_BOUNDS) && (SPCIES_TERMINAL == 0 || SPCIES_TERMINAL == 1)
+#if defined(SCALAR_RHO) && !defined(VAR_BOUNDS)
 #define SPCIES_ADMM_MMA_ELIGIBLE 1
 #else
 #define SPCIES_ADMM_MMA_ELIGIBLE 0
@@ -50,7 +50,10 @@ struct alignas(16) MmaTables {
     double FWb[N][32], BWb[N][32];
     double Hi[8];             // inverse of the (diagonal) Hessian + rho, by column of z; the same for every block (checked on the host)
     double HiN[64], NHiN[64]; // laxMPC: the dense terminal block Hi_N and its negative, [output column][input column] (x columns)
-    double Tm[8][8];          // laxMPC: T by component (qT = T xr, computed per instance at refill)
+    double Tm[8][8];          // laxMPC / ellipMPC: T by component (qT = T xr, computed per instance at refill)
+    // ellipMPC (terminal ellipsoid (v - c)' P (v - c) <= r^2 in the P^(1/2) metric): P_half, -rho P, rho_i Pinv_half, P by column
+    double Ph[64], NRP[64], PihR[64], Pm[64];
+    double cvec[8], rr, rv;   // centre by column, r^2, r
     double Qs[8];             // q = Qs o [xr; ur]   (Q, R stored negated)
     double LB[8], UB[8];
     int xat[8], uat[8];
@@ -70,6 +73,13 @@ static inline bool fill_mma_tables(const spcies_consts &C, MmaTables &T) {
             if (C.Hi[l][j] != C.Hi[0][j]) return false;
     for (int j = 0; j < m; ++j)
         if (C.Hi_0[j] != C.Hi[0][n + j]) return false;
+#if SPCIES_TERMINAL == 2
+    for (int l = 0; l < N - 1; ++l)          // the engine keeps one set of bounds: they must not depend on the stage
+        for (int j = 0; j < nm; ++j)
+            if (C.LBz[l][j] != C.LBz[0][j] || C.UBz[l][j] != C.UBz[0][j]) return false;
+    for (int j = 0; j < m; ++j)
+        if (C.LBu0[j] != C.LBz[0][n + j] || C.UBu0[j] != C.UBz[0][n + j]) return false;
+#endif
     for (int c = 0; c < 8; ++c) {
         T.xat[c] = L::x_at(c);
         T.uat[c] = L::u_at(c);
@@ -79,23 +89,40 @@ static inline bool fill_mma_tables(const spcies_consts &C, MmaTables &T) {
         if (z < 0) continue;
         T.Hi[c] = (double)C.Hi[0][z];
         T.Qs[c] = z < n ? (double)C.Q[z] : (double)C.R[z - n];
+#if SPCIES_TERMINAL == 2
+        T.LB[c] = (double)C.LBz[0][z];
+        T.UB[c] = (double)C.UBz[0][z];
+#else
         T.LB[c] = (double)C.LB[z];
         T.UB[c] = (double)C.UB[z];
+#endif
     }
     for (int oc = 0; oc < 8; ++oc)
         for (int ic = 0; ic < 8; ++ic) {
             if (L::x_at(oc) >= 0 && L::z_at(ic) >= 0) T.NAB[oc * 8 + ic] = -(double)C.AB[L::x_at(oc)][L::z_at(ic)];
             if (L::z_at(oc) >= 0 && L::x_at(ic) >= 0) T.ABt[oc * 8 + ic] = (double)C.AB[L::x_at(ic)][L::z_at(oc)];
         }
-#if SPCIES_TERMINAL == 1
+#if SPCIES_TERMINAL != 0
     for (int oc = 0; oc < 8; ++oc)
         for (int ic = 0; ic < 8; ++ic)
             if (L::x_at(oc) >= 0 && L::x_at(ic) >= 0) {
-                T.HiN[oc * 8 + ic] = (double)C.Hi_N[L::x_at(oc)][L::x_at(ic)];
-                T.NHiN[oc * 8 + ic] = -(double)C.Hi_N[L::x_at(oc)][L::x_at(ic)];
+                const int i = L::x_at(oc), j = L::x_at(ic);
+                T.HiN[oc * 8 + ic] = (double)C.Hi_N[i][j];
+                T.NHiN[oc * 8 + ic] = -(double)C.Hi_N[i][j];
+#if SPCIES_TERMINAL == 2
+                T.Ph[oc * 8 + ic] = (double)C.P_half[i][j];
+                T.NRP[oc * 8 + ic] = -(double)C.P[i][j] * (double)rho;
+                T.PihR[oc * 8 + ic] = (double)C.Pinv_half[i][j] * (double)rho_i;
+                T.Pm[oc * 8 + ic] = (double)C.P[i][j];
+#endif
             }
     for (int i = 0; i < n; ++i)
         for (int j = 0; j < n; ++j) T.Tm[i][j] = (double)C.T[i][j];
+#if SPCIES_TERMINAL == 2
+    for (int c = 0; c < 8; ++c) T.cvec[c] = L::x_at(c) >= 0 ? (double)C.c[L::x_at(c)] : 0.0;
+    T.rr = (double)C.r * (double)C.r;
+    T.rv = (double)C.r;
+#endif
 #endif
     typedef double Blk[n][n];
     Blk *Linv = new Blk[4 * N], *F = Linv + N, *Uinv = F + N, *G = Uinv + N;
@@ -147,9 +174,14 @@ __global__ void __launch_bounds__(MMA_BLOCK, 1) admm_mma_kernel(const BatchIO io
     int k = 0;
     bool live = false, drained = false;
     double q[2] = {0, 0}, nx0[2] = {0, 0}, nxr[2] = {0, 0};   // laxMPC: nxr holds qT = T xr instead of -xr
-#if SPCIES_TERMINAL == 1
+#if SPCIES_TERMINAL != 0
     const double2 hin = reinterpret_cast<const double2 *>(T->HiN)[lane], nhin = reinterpret_cast<const double2 *>(T->NHiN)[lane];
     const double tolxs[2] = {xs[0] ? (double)tol : 1e300, xs[1] ? (double)tol : 1e300};
+#endif
+#if SPCIES_TERMINAL == 2
+    const double2 ph = reinterpret_cast<const double2 *>(T->Ph)[lane], nrp = reinterpret_cast<const double2 *>(T->NRP)[lane];
+    const double2 pihr = reinterpret_cast<const double2 *>(T->PihR)[lane], pm = reinterpret_cast<const double2 *>(T->Pm)[lane];
+    const double cv[2] = {T->cvec[cc[0]], T->cvec[cc[1]]}, r_ = T->rv, rr_ = T->rr;
 #endif
 
     for (;;) {
@@ -171,7 +203,7 @@ __global__ void __launch_bounds__(MMA_BLOCK, 1) admm_mma_kernel(const BatchIO io
                         const double ur_ = us[i] ? io.ur[inst * m + ue[i]] : 0.0;
                         q[i] = qs[i] * (xs[i] ? xr_ : ur_);
                         nx0[i] = xs[i] ? -io.x0[inst * n + xe[i]] : 0.0;
-#if SPCIES_TERMINAL == 1
+#if SPCIES_TERMINAL != 0
                         double qt = 0.0;                                   // qT = T xr (T dense, negated)   code_laxMPC_ADMM_C.c:292-295
                         if (xs[i])
                             for (int j = 0; j < n; ++j) qt = fma(T->Tm[xe[i]][j], io.xr[inst * n + j], qt);
@@ -197,8 +229,8 @@ __global__ void __launch_bounds__(MMA_BLOCK, 1) admm_mma_kernel(const BatchIO io
 
         // ================= pass A: q_hat -> s -> r.h.s. -> forward recurrence =================
         double mup[N][2];   // mu'_b (with the second copies of x_4.. in register 1 of lanes 2,3)
-#if SPCIES_TERMINAL == 1
-        double zNh[2] = {0.0, 0.0};   // z_N_hat = qT + lambda_N - rho v_N
+#if SPCIES_TERMINAL != 0
+        double zNh[2] = {0.0, 0.0};   // z_N_hat = qT + lambda_N - rho v_N  (ellipMPC: in the P^(1/2) metric)
 #endif
         {
             double sp[2];   // s_{b}
@@ -228,6 +260,14 @@ __global__ void __launch_bounds__(MMA_BLOCK, 1) admm_mma_kernel(const BatchIO io
                         const double2 v = LDV(N), la = LDL(N);
                         zNh[0] = xs[0] ? fma(-rho_, v.x, nxr[0] + la.x) : 0.0;
                         zNh[1] = xs[1] ? fma(-rho_, v.y, nxr[1] + la.y) : 0.0;
+                        mma::mv(s[j + 1], hin, zNh, 0.0, 0.0);
+#elif SPCIES_TERMINAL == 2
+                        // ellipMPC: z_N_hat = qT + P_half lambda_N - rho P v_N;  s_N = Hi_N z_N_hat   code_ellipMPC_ADMM_C.c:146-155
+                        const double2 v = LDV(N), la = LDL(N);
+                        const double lav[2] = {la.x, la.y}, vv[2] = {v.x, v.y};
+                        double t_[2];
+                        mma::mv(t_, ph, lav, nxr[0], nxr[1]);
+                        mma::mv(zNh, nrp, vv, t_[0], t_[1]);
                         mma::mv(s[j + 1], hin, zNh, 0.0, 0.0);
 #else
                         s[j + 1][0] = nxr[0];           // :351-353
@@ -285,6 +325,33 @@ __global__ void __launch_bounds__(MMA_BLOCK, 1) admm_mma_kernel(const BatchIO io
             ln.y = xs[1] ? fma(rho_, d1, la.y) : 0.0;
             st[(2 * N) * 32] = vn;
             st[(2 * N + 1) * 32] = ln;
+        }
+#elif SPCIES_TERMINAL == 2
+        {   // terminal block with the radial projection onto the ellipsoid in the P metric   code_ellipMPC_ADMM_C.c:319-351, :375-387
+            const double aux[2] = {fma(-maskx[0], mu[0], zNh[0]), fma(-maskx[1], mu[1], zNh[1])};
+            double zn[2], vn[2], a2[2], ln[2];
+            mma::mv(zn, nhin, aux, 0.0, 0.0);
+            const double2 v = LDV(N), la = LDL(N);
+            const double lav[2] = {la.x, la.y};
+            mma::mv(vn, pihr, lav, zn[0], zn[1]);                                  // z_N + Pinv_half (lambda_N / rho)
+            double dv[2] = {vn[0] - cv[0], vn[1] - cv[1]};
+            mma::mv(a2, pm, dv, 0.0, 0.0);                                         // P (v - c)
+            double vPv = (xs[0] ? dv[0] * a2[0] : 0.0) + (xs[1] ? dv[1] * a2[1] : 0.0);
+            vPv += __shfl_xor_sync(FULL, vPv, 1);
+            vPv += __shfl_xor_sync(FULL, vPv, 2);
+            if (vPv > rr_) {
+                const double sc = r_ / sqrt(vPv);
+                vn[0] = fma(sc, dv[0], cv[0]);
+                vn[1] = fma(sc, dv[1], cv[1]);
+            }
+            vn[0] = xs[0] ? vn[0] : 0.0;
+            vn[1] = xs[1] ? vn[1] : 0.0;
+            const double a3[2] = {xs[0] ? rho_ * (zn[0] - vn[0]) : 0.0, xs[1] ? rho_ * (zn[1] - vn[1]) : 0.0};
+            mma::mv(ln, ph, a3, la.x, la.y);                                       // lambda_N + P_half rho (z_N - v_N)
+            over = over || (fabs(v.x - vn[0]) > tolxs[0]) || (fabs(zn[0] - vn[0]) > tolxs[0]) || (fabs(v.y - vn[1]) > tolxs[1]) ||
+                   (fabs(zn[1] - vn[1]) > tolxs[1]);
+            st[(2 * N) * 32] = make_double2(vn[0], vn[1]);
+            st[(2 * N + 1) * 32] = make_double2(xs[0] ? ln[0] : 0.0, xs[1] ? ln[1] : 0.0);
         }
 #endif
         double u0v[2] = {0, 0};

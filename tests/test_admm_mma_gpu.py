@@ -9,7 +9,7 @@ from spcies_b200 import prebuilt, sysmodel
 from spcies_b200.solver import ARITH_EXACT, ARITH_FAST, ENGINE_MMA, ENGINE_SCALAR, SpciesCudaError
 
 pytestmark = pytest.mark.gpu
-ADMM = ['T_equMPC_ADMM', 'C3_equMPC_ADMM', 'T_laxMPC_ADMM']      # equMPC and laxMPC (terminal block) run on the engine
+ADMM = ['T_equMPC_ADMM', 'C3_equMPC_ADMM', 'T_laxMPC_ADMM', 'T_ellipMPC_ADMM']   # equMPC, laxMPC (terminal block), ellipMPC (terminal ellipsoid)
 
 
 def _ref(name):
@@ -86,14 +86,11 @@ def _per_instance_bounds(name):
 
 
 def test_admm_mma_engine_is_refused_where_it_cannot_run():
-    batchcfg = prebuilt.get('T_ellipMPC_ADMM')
-    sol, spec, cfg = batchcfg
-    batch = sysmodel.synthetic_batch(cfg['sys'], 64, seed=54)
-    with pytest.raises(SpciesCudaError):                                  # terminal ellipsoid: scalar kernel only
-        sol.solve_batch(batch['x0'], batch['xr'], batch['ur'], engine=ENGINE_MMA)
-    sol.solve_batch(batch['x0'], batch['xr'], batch['ur'])
+    """EXACT arithmetic and the debug payload belong to the scalar kernel: asking for MMA there is an error."""
     sol, spec, cfg = prebuilt.get('T_equMPC_ADMM')
+    batch = sysmodel.synthetic_batch(cfg['sys'], 64, seed=54)
     with pytest.raises(SpciesCudaError):
         sol.solve_batch(batch['x0'], batch['xr'], batch['ur'], arith=ARITH_EXACT, engine=ENGINE_MMA)
     with pytest.raises(SpciesCudaError):
         sol.solve_batch(batch['x0'], batch['xr'], batch['ur'], engine=ENGINE_MMA, want_sol=True)
+    sol.solve_batch(batch['x0'], batch['xr'], batch['ur'], arith=ARITH_EXACT)

@@ -5,7 +5,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from spcies_b200 import prebuilt, sysmodel
 SCALE = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
-for name, B in (('C2_laxMPC_FISTA', 700), ('T_equMPC_FISTA', 300), ('C3_equMPC_ADMM', 300), ('C4_ellipMPC_ADMM_soc', 300),
+for name, B in (('C2_laxMPC_FISTA', 700), ('T_equMPC_FISTA', 300), ('C3_equMPC_ADMM', 300), ('T_laxMPC_ADMM', 200), ('T_ellipMPC_ADMM', 120), ('C4_ellipMPC_ADMM_soc', 300),
                 ('C5b_MPCT_EADMM', 40), ('C5a_HMPC_SADMM_split', 24), ('T_HMPC_ADMM_split', 100)):
     sol, spec, cfg = prebuilt.get(name)
     B = max(9, int(B * SCALE))

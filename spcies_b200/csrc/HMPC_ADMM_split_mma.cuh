@@ -297,11 +297,13 @@ __global__ void __launch_bounds__(MMA_BLOCK, 1) hmpc_mma_kernel(const BatchIO io
 #pragma unroll
                 for (int b = 0; b < NBZ; ++b) update_z(t + b, acc[b]);
             }
-#pragma unroll 1
-            for (; t < ZT; ++t) {
-                double acc[1][2];
-                hmpc_product<1, PFZ>(frag + ((size_t)t * NIN) * 32 + lane, st + BLK_QH * 32, ring, acc);
-                update_z(t, acc[0]);
+            // the remaining ZT % NBZ tiles of z in one pass of their own (a single-tile pass would be a 2 NIN-deep dependent chain)
+            constexpr int REM = ZT % NBZ;
+            if constexpr (REM > 0) {
+                double acc[REM][2];
+                hmpc_product<REM, PFZ>(frag + ((size_t)t * NIN) * 32 + lane, st + BLK_QH * 32, ring, acc);
+#pragma unroll
+                for (int b = 0; b < REM; ++b) update_z(t + b, acc[b]);
             }
         }
         {   // s, mu: diamond-set projection of each (y_e, y_s, y_c) triple                              :220-225, :241-258, :294-311

@@ -61,3 +61,30 @@ def test_no_cpu_fallback_without_device():
         sol.solve_batch(x0, xr, ur)
     with pytest.raises(SpciesCudaError):
         sol.solve(x0[0], xr[0], ur[0])
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """The Python mirror of spcies_batch_opts / spcies_batch_info (spcies_b200/solver.py) has the size and field offsets of
+    the C structs in include/spcies_cuda.h (compiled here with gcc: the header is plain C)."""
+    import ctypes
+    import os
+    import subprocess
+    from spcies_b200.solver import BatchInfo, BatchOpts
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / 'sz.c'
+    fields_o = ['device', 'n_devices', 'arith', 'device_pointers', 'LB', 'UB', 'stream', 'block_threads', 'grid_blocks', 'tail_mode',
+                'tail_grace', 'engine', 'tail_caps', 'reserved']
+    fields_i = ['kernel_ms', 'launches', 'sum_k', 'block_threads', 'n_devices', 'drain_us', 'parked', 'reserved']
+    body = ''.join(f'printf("o {f} %zu\\n", offsetof(spcies_batch_opts, {f}));\n' for f in fields_o)
+    body += ''.join(f'printf("i {f} %zu\\n", offsetof(spcies_batch_info, {f}));\n' for f in fields_i)
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "spcies_cuda.h"\nint main(void) {\n'
+                   'printf("o sizeof %zu\\n", sizeof(spcies_batch_opts)); printf("i sizeof %zu\\n", sizeof(spcies_batch_info));\n'
+                   + body + 'return 0; }\n')
+    exe = tmp_path / 'sz'
+    subprocess.run(['gcc', '-I', os.path.join(root, 'include'), str(src), '-o', str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout
+    for line in out.splitlines():
+        which, name, val = line.split()
+        cls = BatchOpts if which == 'o' else BatchInfo
+        expect = ctypes.sizeof(cls) if name == 'sizeof' else getattr(cls, name).offset
+        assert int(val) == expect, (which, name, val, expect)

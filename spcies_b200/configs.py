@@ -93,3 +93,18 @@ def bounds_variant(sys, s: int):
     sys2['UBx'][:sys['p']] = rng.uniform(0.25, 0.35, size=sys['p'])
     sys2['LBu'] = -rng.uniform(0.5, 0.8, size=sys['m'])
     return sys2
+
+
+def per_stage_bounds(sys, N: int):
+    """Bounds that tighten along the horizon, one column per stage 0..N (the reference's per-stage bound matrices): the position
+    upper bounds shrink from their value to 85 % of it, the input bounds from theirs to 75 %."""
+    sys2 = dict(sys)
+    w = np.linspace(1.0, 0.0, N + 1)
+    p = sys['p']
+    UBx = np.repeat(np.asarray(sys['UBx'], float)[:, None], N + 1, axis=1)
+    LBx = np.repeat(np.asarray(sys['LBx'], float)[:, None], N + 1, axis=1)
+    UBx[:p] *= 0.85 + 0.15 * w
+    UBu = np.repeat(np.asarray(sys['UBu'], float)[:, None], N + 1, axis=1) * (0.75 + 0.25 * w)
+    LBu = np.repeat(np.asarray(sys['LBu'], float)[:, None], N + 1, axis=1) * (0.75 + 0.25 * w)
+    sys2.update(LBx=LBx, UBx=UBx, LBu=LBu, UBu=UBu)
+    return sys2

@@ -55,7 +55,7 @@ constexpr long long MMA_BULK_MIN = 16LL * 148 * (MMA_BLOCK_BULK / 4);   // batch
                                           // slower (tools/variants.py: 10.6 ms at 384 threads, 11.7 ms at 512, against 10.1 ms): the
                                           // stage-batched products of pass A, not the iterates, hold the registers, so it still spills
 #endif
-constexpr bool HAS_MMA = SPCIES_FISTA_MMA != 0 && sizeof(real) == 8 && nm <= 8 && N >= 2 && N <= 12;
+constexpr bool MMA_SHAPE_OK = SPCIES_FISTA_MMA != 0 && sizeof(real) == 8 && nm <= 8 && N >= 2 && N <= 12;
 constexpr int MMA_KTAB = k_max + 2;
 constexpr bool PRESCALE = SPCIES_FISTA_MMA_PRESCALE != 0;
 
@@ -113,6 +113,8 @@ struct alignas(16) MmaTables {
 constexpr size_t MMA_BYTES = (sizeof(MmaTables) + 15) / 16 * 16;
 constexpr size_t MMA_OFFSET = BLOB_BYTES;                 // position in the device constant blob
 constexpr size_t TOTAL_BLOB_BYTES = BLOB_BYTES + MMA_BYTES;
+// the tables (the momentum table has k_max + 2 entries) must fit shared memory; otherwise the scalar kernel runs
+constexpr bool HAS_MMA = MMA_SHAPE_OK && MMA_BYTES <= 200 * 1024;
 constexpr bool BULK_SS = SPCIES_FISTA_MMA_BULK_SMEM != 0 && MERGE;
 constexpr size_t MMA_BULK_SMEM = MMA_BYTES + (BULK_SS ? (size_t)2 * N * MMA_BLOCK_BULK * sizeof(double2) : 0);
 

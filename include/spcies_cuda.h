@@ -18,6 +18,8 @@
  *   ellipMPC_ADMM       formulations/+ellipMPC/header_ellipMPC_ADMM_C.h      (code_ellipMPC_ADMM_C.c)
  *   ellipMPC_ADMM_soc   formulations/+ellipMPC/header_ellipMPC_ADMM_soc_C.h  (code_ellipMPC_ADMM_soc_C.c:20)
  *   MPCT_EADMM          formulations/+MPCT/header_MPCT_EADMM_C.h             (code_MPCT_EADMM_C.c:18)
+ *   MPCT_ADMM_cs        formulations/+MPCT/header_MPCT_ADMM_cs_C.h:25        (code_MPCT_ADMM_cs_C.c:18)
+ *   MPCT_ADMM_semiband  formulations/+MPCT/header_MPCT_ADMM_semiband_C.h     (code_MPCT_ADMM_semiband_C.c:21)
  *   HMPC_ADMM           formulations/+HMPC/header_HMPC_ADMM_split_C.h:27     (code_HMPC_ADMM_split_C.c:19)
  *
  * Conventions
@@ -147,7 +149,9 @@ const char *spcies_cuda_last_error(void);
  *   SPCIES_CUDA_SOLVER(ellipMPC_ADMM)      ellipMPC_ADMM       ellipMPC_ADMM_batch
  *   SPCIES_CUDA_SOLVER_R(ellipMPC_ADMM_soc) ellipMPC_ADMM_soc  ellipMPC_ADMM_soc_batch
  *   SPCIES_CUDA_SOLVER(MPCT_EADMM)         MPCT_EADMM          MPCT_EADMM_batch
- *   SPCIES_CUDA_SOLVER(HMPC_ADMM)          HMPC_ADMM           HMPC_ADMM_batch   (ADMM_split and SADMM_split)
+ *   SPCIES_CUDA_SOLVER(MPCT_ADMM_cs)       MPCT_ADMM_cs        MPCT_ADMM_cs_batch
+ *   SPCIES_CUDA_SOLVER(MPCT_ADMM_semiband) MPCT_ADMM_semiband  MPCT_ADMM_semiband_batch
+ *   SPCIES_CUDA_SOLVER(HMPC_ADMM)          HMPC_ADMM           HMPC_ADMM_batch   (ADMM, ADMM_split and SADMM_split)
  */
 
 #ifdef __cplusplus

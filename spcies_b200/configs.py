@@ -50,6 +50,11 @@ def reference_test(name: str, N: int = 10, **solver_overrides):
         param = dict(Q=Q, R=R, T=10.0 * Q, S=R, N=N)
         so = dict(rho_base=2.0, rho_mult=20.0, k_max=5000, tol=1e-7)
         kw = dict(formulation='MPCT', method='EADMM')
+    elif name == 'MPCT_ADMM_cs':
+        # tests/test_MPCT_ADMM.m:6-17 (its rho_base / rho_mult are ignored by this solver: rho stays at the default 1e-2)
+        param = dict(Q=Q, R=R, T=10.0 * Q, S=R, N=N)
+        so = dict(rho_base=2.0, rho_mult=20.0, k_max=5000, tol=1e-7)
+        kw = dict(formulation='MPCT', method='ADMM', submethod='cs')
     elif name in ('HMPC_ADMM_split', 'HMPC_SADMM_split'):
         param = dict(Q=Q, R=R, N=N, w=3 * 1.627 * 0.2, Te=10.0 * N * Q, Se=R)
         param['Th'] = param['Te']

@@ -69,11 +69,11 @@ struct Solver {
             real x0[n], xr[n], ur[m];
 #pragma unroll
             for (int i = 0; i < n; ++i) {
-                x0[i] = (real)io.x0[inst * n + i];
-                xr[i] = (real)io.xr[inst * n + i];
+                x0[i] = (real)eng_x(C, io.x0, inst, n, i);
+                xr[i] = (real)eng_x(C, io.xr, inst, n, i);
             }
 #pragma unroll
-            for (int i = 0; i < m; ++i) ur[i] = (real)io.ur[inst * m + i];
+            for (int i = 0; i < m; ++i) ur[i] = (real)eng_u(C, io.ur, inst, m, i);
 #pragma unroll
             for (int j = 0; j < n; ++j) {
                 real b = real(0), qe = real(0), qc = real(0);
@@ -186,7 +186,7 @@ struct Solver {
 
         __device__ void finish(long long inst, int k, int ef) {
 #pragma unroll
-            for (int j = 0; j < m; ++j) io.u[inst * m + j] = (double)s.ld(OFF_P + j);   // u_opt = z[0..m)   :359-368
+            for (int j = 0; j < m; ++j) io.u[inst * m + j] = eng_u_out(C, (double)s.ld(OFF_P + j), j);   // u_opt = z[0..m)   :359-368
             io.k[inst] = k;
             io.e[inst] = ef;
             if (io.sol) {   // sol_<name>: z, s, z_hat, s_hat, lambda, mu (header_HMPC_ADMM_split_C.h)

@@ -209,11 +209,11 @@ __global__ void __launch_bounds__(MMA_BLOCK, 1) hmpc_mma_kernel(const BatchIO io
                     double x0[n], xr[n], ur[m];
 #pragma unroll
                     for (int i = 0; i < n; ++i) {
-                        x0[i] = io.x0[inst * n + i];
-                        xr[i] = io.xr[inst * n + i];
+                        x0[i] = eng_x(C, io.x0, inst, n, i);
+                        xr[i] = eng_x(C, io.xr, inst, n, i);
                     }
 #pragma unroll
-                    for (int i = 0; i < m; ++i) ur[i] = io.ur[inst * m + i];
+                    for (int i = 0; i < m; ++i) ur[i] = eng_u(C, io.ur, inst, m, i);
 #pragma unroll
                     for (int i = 0; i < 2; ++i) {
                         const int c = 2 * t4 + i;
@@ -344,8 +344,8 @@ __global__ void __launch_bounds__(MMA_BLOCK, 1) hmpc_mma_kernel(const BatchIO io
             const int ef = !gover ? 1 : ((k >= k_max) ? -1 : 0);
             if (ef != 0) {
                 const double2 z0 = LD(BLK_P + 0);                        // u_opt = z[0..m)   (:359-368)
-                if (2 * t4 < m) io.u[inst * m + 2 * t4] = z0.x;
-                if (2 * t4 + 1 < m) io.u[inst * m + 2 * t4 + 1] = z0.y;
+                if (2 * t4 < m) io.u[inst * m + 2 * t4] = eng_u_out(C, z0.x, 2 * t4);
+                if (2 * t4 + 1 < m) io.u[inst * m + 2 * t4 + 1] = eng_u_out(C, z0.y, 2 * t4 + 1);
                 if (leader) {
                     io.k[inst] = k;
                     io.e[inst] = ef;

@@ -51,11 +51,11 @@ struct Solver {
         __device__ void init(long long inst) {
 #pragma unroll
             for (int i = 0; i < n; ++i) {
-                s.st(OFF_X0 + i, (real)io.x0[inst * n + i]);
-                s.st(OFF_XR + i, (real)io.xr[inst * n + i]);
+                s.st(OFF_X0 + i, (real)eng_x(C, io.x0, inst, n, i));
+                s.st(OFF_XR + i, (real)eng_x(C, io.xr, inst, n, i));
             }
 #pragma unroll
-            for (int i = 0; i < m; ++i) s.st(OFF_UR + i, (real)io.ur[inst * m + i]);
+            for (int i = 0; i < m; ++i) s.st(OFF_UR + i, (real)eng_u(C, io.ur, inst, m, i));
 #pragma unroll 4
             for (int e = 0; e < OFF_MU; ++e) s.st(e, real(0));   // z1 = z3 = lambda = z2 = 0
         }
@@ -255,7 +255,7 @@ struct Solver {
 
         __device__ void finish(long long inst, int k, int ef) {
 #pragma unroll
-            for (int j = 0; j < m; ++j) io.u[inst * m + j] = (double)s.ld(OFF_Z1 + n + j);   // u_opt = z1[0][n..]  :470-478
+            for (int j = 0; j < m; ++j) io.u[inst * m + j] = eng_u_out(C, (double)s.ld(OFF_Z1 + n + j), j);   // u_opt = z1[0][n..]  :470-478
             io.k[inst] = k;
             io.e[inst] = ef;
             if (io.sol) {   // sol_<name>: z1, z2, z3, lambda (header_MPCT_EADMM_C.h); lambda written in full [l][j] order

@@ -101,6 +101,8 @@ __global__ void __launch_bounds__(MMA_BLOCK, 1) eadmm_mma_kernel(const BatchIO i
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint64_t mbar;
+    const spcies_consts *C = reinterpret_cast<const spcies_consts *>(g_blob);   // engineering-unit scaling only
+    (void)C;
     const MmaSmall *T = reinterpret_cast<const MmaSmall *>(smem_raw);
     stage_constants(smem_raw, g_blob + MMA_OFFSET, (uint32_t)MMA_STAGED, &mbar);
     const MmaFrag *Fr = FRAG_SMEM ? reinterpret_cast<const MmaFrag *>(smem_raw + SMALL_BYTES)
@@ -156,8 +158,8 @@ __global__ void __launch_bounds__(MMA_BLOCK, 1) eadmm_mma_kernel(const BatchIO i
                     inst = slot;
 #pragma unroll
                     for (int i = 0; i < 2; ++i) {
-                        x0v[i] = xs[i] ? io.x0[inst * n + xe[i]] : 0.0;       // x0 zero-padded to nm (:35)
-                        ref[i] = xs[i] ? io.xr[inst * n + xe[i]] : (us[i] ? io.ur[inst * m + ue[i]] : 0.0);
+                        x0v[i] = xs[i] ? eng_x(C, io.x0, inst, n, xe[i]) : 0.0;       // x0 zero-padded to nm (:35)
+                        ref[i] = xs[i] ? eng_x(C, io.xr, inst, n, xe[i]) : (us[i] ? eng_u(C, io.ur, inst, m, ue[i]) : 0.0);
                     }
 #pragma unroll 4
                     for (int e = 0; e < MMA_NBLK; ++e) ST(e, make_double2(0.0, 0.0));
@@ -360,8 +362,8 @@ __global__ void __launch_bounds__(MMA_BLOCK, 1) eadmm_mma_kernel(const BatchIO i
         if (live) {
             const int ef = !gover ? 1 : ((k >= k_max) ? -1 : 0);
             if (ef != 0) {
-                if (us[0]) io.u[inst * m + ue[0]] = z10.x;                  // u_opt = z1[0][n..]  (:470-478)
-                if (us[1]) io.u[inst * m + ue[1]] = z10.y;
+                if (us[0]) io.u[inst * m + ue[0]] = eng_u_out(C, z10.x, ue[0]);                  // u_opt = z1[0][n..]  (:470-478)
+                if (us[1]) io.u[inst * m + ue[1]] = eng_u_out(C, z10.y, ue[1]);
                 if (leader) {
                     io.k[inst] = k;
                     io.e[inst] = ef;

@@ -153,11 +153,11 @@ struct Solver {
             real x0[n], xr[n], ur[m];
 #pragma unroll
             for (int i = 0; i < n; ++i) {
-                x0[i] = (real)io.x0[inst * n + i];
-                xr[i] = (real)io.xr[inst * n + i];
+                x0[i] = (real)eng_x(C, io.x0, inst, n, i);
+                xr[i] = (real)eng_x(C, io.xr, inst, n, i);
             }
 #pragma unroll
-            for (int i = 0; i < m; ++i) ur[i] = (real)io.ur[inst * m + i];
+            for (int i = 0; i < m; ++i) ur[i] = (real)eng_u(C, io.ur, inst, m, i);
 #pragma unroll
             for (int j = 0; j < n; ++j) {
                 real b = real(0);
@@ -427,7 +427,7 @@ struct Solver {
         // u_opt = v_0 (the clipped copy, :557-566); debug payload z (written during the last pass B), v, lambda
         __device__ void finish(long long inst, int k, int ef) {
 #pragma unroll
-            for (int j = 0; j < m; ++j) io.u[inst * m + j] = (double)s.ld(OFF_V + j);
+            for (int j = 0; j < m; ++j) io.u[inst * m + j] = eng_u_out(C, (double)s.ld(OFF_V + j), j);
             io.k[inst] = k;
             io.e[inst] = ef;
             if (sol) {

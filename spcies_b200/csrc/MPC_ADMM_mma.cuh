@@ -138,6 +138,8 @@ __global__ void __launch_bounds__(MMA_BLOCK, 1) admm_mma_kernel(const BatchIO io
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint64_t mbar;
+    const spcies_consts *C = reinterpret_cast<const spcies_consts *>(g_blob);   // engineering-unit scaling only
+    (void)C;
     const MmaTables *T = reinterpret_cast<const MmaTables *>(smem_raw);
     stage_constants(smem_raw, g_blob + MMA_OFFSET, (uint32_t)MMA_BYTES, &mbar);
 
@@ -199,14 +201,14 @@ __global__ void __launch_bounds__(MMA_BLOCK, 1) admm_mma_kernel(const BatchIO io
                     inst = slot;
 #pragma unroll
                     for (int i = 0; i < 2; ++i) {
-                        const double xr_ = xs[i] ? io.xr[inst * n + xe[i]] : 0.0;
-                        const double ur_ = us[i] ? io.ur[inst * m + ue[i]] : 0.0;
+                        const double xr_ = xs[i] ? eng_x(C, io.xr, inst, n, xe[i]) : 0.0;
+                        const double ur_ = us[i] ? eng_u(C, io.ur, inst, m, ue[i]) : 0.0;
                         q[i] = qs[i] * (xs[i] ? xr_ : ur_);
-                        nx0[i] = xs[i] ? -io.x0[inst * n + xe[i]] : 0.0;
+                        nx0[i] = xs[i] ? -eng_x(C, io.x0, inst, n, xe[i]) : 0.0;
 #if SPCIES_TERMINAL != 0
                         double qt = 0.0;                                   // qT = T xr (T dense, negated)   code_laxMPC_ADMM_C.c:292-295
                         if (xs[i])
-                            for (int j = 0; j < n; ++j) qt = fma(T->Tm[xe[i]][j], io.xr[inst * n + j], qt);
+                            for (int j = 0; j < n; ++j) qt = fma(T->Tm[xe[i]][j], eng_x(C, io.xr, inst, n, j), qt);
                         nxr[i] = qt;
 #else
                         nxr[i] = -xr_;
@@ -404,7 +406,7 @@ __global__ void __launch_bounds__(MMA_BLOCK, 1) admm_mma_kernel(const BatchIO io
             if (ef != 0) {
 #pragma unroll
                 for (int i = 0; i < 2; ++i)
-                    if (us[i]) io.u[inst * m + ue[i]] = u0v[i];                               // u_opt = v_0   (:557-566)
+                    if (us[i]) io.u[inst * m + ue[i]] = eng_u_out(C, u0v[i], ue[i]);                               // u_opt = v_0   (:557-566)
                 if (leader) {
                     io.k[inst] = k;
                     io.e[inst] = ef;

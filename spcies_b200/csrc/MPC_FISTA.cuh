@@ -433,11 +433,11 @@ __global__ void __launch_bounds__(BLOCK, 1) fista_kernel(const BatchIO io, const
                 real x0[n], xr[n], ur[m];
 #pragma unroll
                 for (int i = 0; i < n; ++i) {
-                    x0[i] = (real)io.x0[inst * n + i];
-                    xr[i] = (real)io.xr[inst * n + i];
+                    x0[i] = (real)eng_x(C, io.x0, inst, n, i);
+                    xr[i] = (real)eng_x(C, io.xr, inst, n, i);
                 }
 #pragma unroll
-                for (int i = 0; i < m; ++i) ur[i] = (real)io.ur[inst * m + i];
+                for (int i = 0; i < m; ++i) ur[i] = (real)eng_u(C, io.ur, inst, m, i);
 #pragma unroll
                 for (int j = 0; j < n; ++j) {
                     real b = real(0);
@@ -591,7 +591,7 @@ __global__ void __launch_bounds__(BLOCK, 1) fista_kernel(const BatchIO io, const
             else if (k >= k_max) ef = -1;
             if (ef != 0) {
 #pragma unroll
-                for (int j = 0; j < m; ++j) io.u[inst * m + j] = (double)u0[j];
+                for (int j = 0; j < m; ++j) io.u[inst * m + j] = eng_u_out(C, (double)u0[j], j);
                 io.k[inst] = k;
                 io.e[inst] = ef;
                 stat_k += (unsigned long long)k;

@@ -228,6 +228,8 @@ __global__ void __launch_bounds__(BLOCK, 1) fista_mma_kernel(const BatchIO io, c
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint64_t mbar;
+    const spcies_consts *C = reinterpret_cast<const spcies_consts *>(g_blob);   // engineering-unit scaling only
+    (void)C;
     const MmaTables *T = reinterpret_cast<const MmaTables *>(smem_raw);
     stage_constants(smem_raw, g_blob + MMA_OFFSET, (uint32_t)MMA_BYTES, &mbar);
 
@@ -343,8 +345,8 @@ __global__ void __launch_bounds__(BLOCK, 1) fista_mma_kernel(const BatchIO io, c
                     inst = resume ? __double_as_longlong(pk[0]) : slot;
 #pragma unroll
                     for (int i = 0; i < 2; ++i) {
-                        const double xr_ = xs[i] ? io.xr[inst * n + xe[i]] : 0.0;
-                        const double ur_ = us[i] ? io.ur[inst * m + ue[i]] : 0.0;
+                        const double xr_ = xs[i] ? eng_x(C, io.xr, inst, n, xe[i]) : 0.0;
+                        const double ur_ = us[i] ? eng_u(C, io.ur, inst, m, ue[i]) : 0.0;
                         q[i] = qs[i] * (xs[i] ? xr_ : ur_);          // QRi o [Q xr; R ur]
                         qT[i] = ts[i] * xr_;                          // Ti o T xr (lax)  |  xr (equ)
                         if (VARB) {
@@ -354,7 +356,7 @@ __global__ void __launch_bounds__(BLOCK, 1) fista_mma_kernel(const BatchIO io, c
                         }
                         double l0, h0;
                         bnd(0, i, l0, h0);
-                        const double x0_ = xs[i] ? io.x0[inst * n + xe[i]] : 0.0;
+                        const double x0_ = xs[i] ? eng_x(C, io.x0, inst, n, xe[i]) : 0.0;
                         lo0[i] = xs[i] ? x0_ : l0;
                         hi0[i] = xs[i] ? x0_ : h0;
                     }
@@ -576,7 +578,7 @@ __global__ void __launch_bounds__(BLOCK, 1) fista_mma_kernel(const BatchIO io, c
             if (ef != 0) {
 #pragma unroll
                 for (int i = 0; i < 2; ++i)
-                    if (us[i]) io.u[inst * m + ue[i]] = u0v[i];
+                    if (us[i]) io.u[inst * m + ue[i]] = eng_u_out(C, u0v[i], ue[i]);
                 if (leader) {
                     io.k[inst] = k;
                     io.e[inst] = ef;

@@ -79,6 +79,32 @@ template <typename T> __device__ __forceinline__ bool exceeds(T x, T tol_) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Engineering units (options.in_engineering): inputs are scaled as `scaling_x[i]*( x0_in[i] - OpPoint_x[i] )`, the control
+// action is returned as `u[j]*scaling_i_u[j] + OpPoint_u[j]` (code_laxMPC_FISTA_C.c:75-82, :398-402; the same block in every
+// template).  Individually rounded operations in both arithmetic modes, as gcc -O3 emits them for x86-64.  `C` is the generated
+// constant struct: it has the five scaling arrays only when the solver was generated with in_engineering (the `#define` decides).
+// ------------------------------------------------------------------------------------------------
+#if defined(in_engineering) && in_engineering == 1
+template <class CT> __device__ __forceinline__ double eng_x(const CT *C, const double *a, long long inst, int n_, int i) {
+    return __dmul_rn((double)C->scaling_x[i], __dsub_rn(a[inst * n_ + i], (double)C->OpPoint_x[i]));
+}
+template <class CT> __device__ __forceinline__ double eng_u(const CT *C, const double *a, long long inst, int m_, int i) {
+    return __dmul_rn((double)C->scaling_u[i], __dsub_rn(a[inst * m_ + i], (double)C->OpPoint_u[i]));
+}
+template <class CT> __device__ __forceinline__ double eng_u_out(const CT *C, double u, int j) {
+    return __dadd_rn(__dmul_rn(u, (double)C->scaling_i_u[j]), (double)C->OpPoint_u[j]);
+}
+#else
+template <class CT> __device__ __forceinline__ double eng_x(const CT *, const double *a, long long inst, int n_, int i) {
+    return a[inst * n_ + i];
+}
+template <class CT> __device__ __forceinline__ double eng_u(const CT *, const double *a, long long inst, int m_, int i) {
+    return a[inst * m_ + i];
+}
+template <class CT> __device__ __forceinline__ double eng_u_out(const CT *, double u, int) { return u; }
+#endif
+
+// ------------------------------------------------------------------------------------------------
 // Per-instance state in shared memory: element-major, thread-minor
 // ------------------------------------------------------------------------------------------------
 template <typename T, int BLOCK> struct State {

@@ -143,3 +143,113 @@ def cons_MPCT_EADMM(recipe) -> SolverSpec:
         ref_header='formulations/+MPCT/header_MPCT_EADMM_C.h',
         sol_fields=(('z1', (N + 1) * nm), ('z2', nm), ('z3', (N + 1) * nm), ('lambda', (N + 3) * nm)),
         vars=v, dims=dict(n=n, m=m, N=N))
+
+
+# --------------------------------------------------------------------------------------
+# ADMM on the extended state space (submethod 'cs', the default of MPCT / ADMM)
+# --------------------------------------------------------------------------------------
+def compute_MPCT_ADMM_cs_ingredients(recipe):
+    """formulations/+MPCT/compute_MPCT_ADMM_cs_ingredients.m:18-195: the state / input are extended with the artificial
+    reference, z_j = (x_j, x_s), v_j = (u_j, u_s); the equality-constrained QP of the z update is solved through the sparse
+    chain  -A Hi (CSR)  ->  L D L' of W = A Hi A' (CSC)  ->  -Hi, -Hi A' (CSR)."""
+    from .. import sp_utils
+    A, B, n, m, N = get_sys_param(recipe)
+    sys, param, opt = recipe.sys, recipe.param, recipe.options
+    nm = n + m
+    Q, R, T, S = (np.asarray(param[k], float) for k in ('Q', 'R', 'T', 'S'))
+    inf = float(opt.inf_value)
+    LBx = np.asarray(sys.get('LBx', -inf * np.ones(n)), float).ravel()
+    UBx = np.asarray(sys.get('UBx', inf * np.ones(n)), float).ravel()
+    LBu = np.asarray(sys.get('LBu', -inf * np.ones(m)), float).ravel()
+    UBu = np.asarray(sys.get('UBu', inf * np.ones(m)), float).ravel()
+    solver = opt.solver
+    rho = solver['rho']
+    if np.isscalar(rho) and solver.get('force_vector_rho', False):
+        rho = float(rho) * np.ones(N * nm)          # (sic) N (n+m) entries, :71 -- half the 2 N (n+m) of the decision vector
+    scalar = bool(np.isscalar(rho))
+
+    Qz = np.block([[Q, -Q], [-Q, Q + T / N]])
+    Rz = np.block([[R, -R], [-R, R + S / N]])
+    H = np.kron(np.eye(N), sla.block_diag(Qz, Rz))
+    Hhat = H + (float(rho) * np.eye(2 * N * nm) if scalar else np.diag(np.asarray(rho, float)))
+
+    Zn, Zm = np.zeros((n, n)), np.zeros((m, m))
+    AA = np.vstack([np.hstack([A, Zn]), np.hstack([Zn, np.eye(n)]), np.zeros((m, 2 * n))])
+    BB = np.vstack([np.hstack([B, np.zeros((n, m))]), np.zeros((n, 2 * m)), np.hstack([Zm, np.eye(m)])])
+    II = np.vstack([np.hstack([-np.eye(n), np.zeros((n, n + 2 * m))]),
+                    np.hstack([Zn, -np.eye(n), np.zeros((n, 2 * m))]),
+                    np.hstack([np.zeros((m, 2 * n + m)), -np.eye(m)])])
+    dn = 2 * n + m                                  # rows per stage
+    dnm = 2 * nm                                    # columns per stage
+    Aeq = sla.block_diag(np.kron(np.eye(N - 1), np.hstack([AA, BB])), np.hstack([A, -np.eye(n), B, np.zeros((n, m))]))
+    for j in range(1, N):                           # the II blocks, one block-column to the right of each [AA BB]
+        r0 = (j - 1) * dn
+        Aeq[r0:r0 + dn, j * dnm:(j + 1) * dnm] = II
+    init_cond = np.vstack([np.hstack([np.eye(n), np.zeros((n, n + 2 * m))]),
+                           np.hstack([Zn, A - np.eye(n), np.zeros((n, m)), B])])
+    Aeq = np.vstack([np.hstack([init_cond, np.zeros((2 * n, Aeq.shape[1] - dnm))]), Aeq])
+
+    eps_x, eps_u = float(solver['epsilon_x']), float(solver['epsilon_u'])
+    LBz = np.concatenate([LBx, LBx + eps_x])
+    UBz = np.concatenate([UBx, UBx - eps_x])
+    LBv = np.concatenate([LBu, LBu + eps_u])
+    UBv = np.concatenate([UBu, UBu - eps_u])
+    LB = np.kron(np.ones(N), np.concatenate([LBz, LBv]))
+    UB = np.kron(np.ones(N), np.concatenate([UBz, UBv]))
+
+    Hinv = np.linalg.inv(Hhat)
+    W = Aeq @ Hinv @ Aeq.T
+    L_val, L_row, L_col, Dinv = sp_utils.full2LDL(W, for_LDLsolve=True)
+    v = dict(n=n, m=m, N=N, rho_is_scalar=scalar)
+    v['Tz'] = -(1.0 / N) * T
+    v['Sz'] = -(1.0 / N) * S
+    v['LB'], v['UB'] = LB, UB
+    v['rho'] = float(rho) if scalar else np.asarray(rho, float)
+    v['rho_i'] = 1.0 / v['rho']
+    v['L_CSC'] = sp_utils.Sparse(val=L_val, row=L_row, col=L_col, nnz=len(L_val), nrow=W.shape[0], ncol=W.shape[0])
+    v['Dinv'] = Dinv
+    v['AHi_CSR'] = sp_utils.full2CSR(-Aeq @ Hinv)
+    v['HiA_CSR'] = sp_utils.full2CSR(-Hinv @ Aeq.T)
+    v['Hi_CSR'] = sp_utils.full2CSR(-Hinv)
+    v.update(scaling_vars(sys, n, m))
+    v['dense'] = dict(Hhat=Hhat, H=H, Aeq=Aeq, W=W, Hinv=Hinv)
+    return v
+
+
+def cons_MPCT_ADMM_cs(recipe) -> SolverSpec:
+    """formulations/+MPCT/cons_MPCT_ADMM_cs_C.m:36-131."""
+    opts = recipe.options
+    v = compute_MPCT_ADMM_cs_ingredients(recipe)
+    n, m, N = v['n'], v['m'], v['N']
+    vopt = var_options(opts)
+    vopt_rho = var_options(opts, array=False) if v['rho_is_scalar'] else vopt
+    prec = opts.precision
+    D = ('define',)
+    defs = default_defines(opts)
+    defs += [Row('nn_', n, True, 'uint', D), Row('mm_', m, True, 'uint', D),
+             Row('nm_', n + m, True, 'uint', D), Row('dnm_', 2 * (n + m), True, 'uint', D),
+             Row('nrow_AHi', v['AHi_CSR'].nrow, True, 'uint', D), Row('nrow_HiA', v['HiA_CSR'].nrow, True, 'uint', D),
+             Row('NN_', N, True, 'uint', D),
+             Row('k_max', int(opts.solver['k_max']), True, 'uint', D),
+             Row('tol', float(opts.solver['tol']), True, prec, D)]
+    if v['rho_is_scalar']:
+        defs.append(Row('SCALAR_RHO', 1, False, 'bool', D))
+    consts = [Row('rho', v['rho'], True, prec, vopt_rho), Row('rho_i', v['rho_i'], True, prec, vopt_rho),
+              Row('Tz', v['Tz'], True, prec, vopt), Row('Sz', v['Sz'], True, prec, vopt),
+              Row('LB', v['LB'], True, prec, vopt), Row('UB', v['UB'], True, prec, vopt),
+              Row('L_val', v['L_CSC'].val, True, prec, vopt), Row('L_col', v['L_CSC'].col, True, 'int', vopt),
+              Row('L_row', v['L_CSC'].row, True, 'int', vopt), Row('Dinv', v['Dinv'], True, prec, vopt)]
+    for nm_ in ('AHi', 'HiA', 'Hi'):
+        s = v[nm_ + '_CSR']
+        consts += [Row(nm_ + '_val', s.val, True, prec, vopt), Row(nm_ + '_col', s.col, True, 'int', vopt),
+                   Row(nm_ + '_row', s.row, True, 'int', vopt)]
+    if opts.in_engineering:
+        consts += engineering_rows(v, prec, vopt)
+    zlen = 2 * N * (n + m)
+    return SolverSpec(
+        formulation='MPCT', method='ADMM', submethod='cs', func_name='MPCT_ADMM_cs', kernel='MPCT_ADMM_cs',
+        defines=defs, constants=consts,
+        ref_code='formulations/+MPCT/code_MPCT_ADMM_cs_C.c',
+        ref_header='formulations/+MPCT/header_MPCT_ADMM_cs_C.h',
+        sol_fields=(('z', zlen), ('v', zlen), ('lambda', zlen)),
+        vars=v, dims=dict(n=n, m=m, N=N, dim=zlen, n_eq=v['AHi_CSR'].nrow))

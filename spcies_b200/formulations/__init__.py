@@ -16,6 +16,7 @@ CONSTRUCTORS = {
     'ellipMPC_ADMM': ellipMPC.cons_ellipMPC_ADMM,
     'ellipMPC_ADMM_soc': ellipMPC.cons_ellipMPC_ADMM_soc,
     'MPCT_EADMM': MPCT.cons_MPCT_EADMM,
+    'MPCT_ADMM_cs': MPCT.cons_MPCT_ADMM_cs,
     'HMPC_ADMM_split': HMPC.cons_HMPC_ADMM_split,
     'HMPC_SADMM_split': HMPC.cons_HMPC_SADMM_split,
 }

@@ -22,7 +22,7 @@ def test_header_lists_common_symbols_and_families():
                            'spcies_cuda_device_count', 'spcies_cuda_kernel_attributes', 'spcies_cuda_free',
                            'spcies_cuda_last_error'}
     assert set(FAMILIES) == {'laxMPC_FISTA', 'laxMPC_ADMM', 'equMPC_FISTA', 'equMPC_ADMM', 'ellipMPC_ADMM',
-                             'ellipMPC_ADMM_soc', 'MPCT_EADMM', 'HMPC_ADMM'}
+                             'ellipMPC_ADMM_soc', 'MPCT_EADMM', 'MPCT_ADMM_cs', 'MPCT_ADMM_semiband', 'HMPC_ADMM'}
 
 
 @pytest.mark.parametrize('name', list(prebuilt.SOLVERS))

@@ -8,7 +8,7 @@ from spcies_b200 import prebuilt, sysmodel
 GOLD = {'T_laxMPC_FISTA': ('laxMPC_FISTA', 'z', 54), 'T_equMPC_FISTA': ('equMPC_FISTA', 'z', 66),
         'T_laxMPC_ADMM': ('laxMPC_ADMM', 'z', 1264), 'T_equMPC_ADMM': ('equMPC_ADMM', 'z', 1271),
         'T_ellipMPC_ADMM': ('ellipMPC_ADMM', 'z', 1278), 'T_ellipMPC_ADMM_soc': ('ellipMPC_ADMM_soc', 'z', 879),
-        'T_MPCT_EADMM': ('MPCT_EADMM', 'z1', 208)}
+        'T_MPCT_EADMM': ('MPCT_EADMM', 'z1', 208), 'T_MPCT_ADMM_cs': ('MPCT_ADMM', 'z', 650)}
 
 
 def _ref(name):

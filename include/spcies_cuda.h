@@ -21,6 +21,8 @@
  *   MPCT_ADMM_cs        formulations/+MPCT/header_MPCT_ADMM_cs_C.h:25        (code_MPCT_ADMM_cs_C.c:18)
  *   MPCT_ADMM_semiband  formulations/+MPCT/header_MPCT_ADMM_semiband_C.h     (code_MPCT_ADMM_semiband_C.c:21)
  *   HMPC_ADMM           formulations/+HMPC/header_HMPC_ADMM_split_C.h:27     (code_HMPC_ADMM_split_C.c:19)
+ *                       formulations/+HMPC/header_HMPC_ADMM_C.h:24           (code_HMPC_ADMM_C.c:18)
+ *                       formulations/+HMPC/header_ellipHMPC_ADMM_C.h:24      (code_ellipHMPC_ADMM_C.c:18, six references)
  *
  * Conventions
  *   - all host arrays are row-major, instance-major: x0[B][nn_], xr[B][nn_], ur[B][mm_], r_ellip[B],
@@ -141,6 +143,16 @@ const char *spcies_cuda_last_error(void);
                      double *u_opt, int *k, int *e_flag, SOL *sol /* [B] or NULL */,                       \
                      const spcies_batch_opts *opts /* or NULL */, spcies_batch_info *info /* or NULL */)
 
+/* ellipHMPC takes three state and three input references, the constant and the two harmonic components of the reference
+ * trajectory (header_ellipHMPC_ADMM_C.h:24; code_ellipHMPC_ADMM_C.c:18) */
+#define SPCIES_CUDA_DECLARE_SOLVER_6REF(NAME, SOL)                                                         \
+    void NAME(double *x0_in, double *xre_in, double *xrs_in, double *xrc_in, double *ure_in, double *urs_in, \
+              double *urc_in, double *u_opt, int *k_in, int *e_flag, SOL *sol);                            \
+    int NAME##_batch(long B, const double *x0, const double *xre, const double *xrs, const double *xrc,   \
+                     const double *ure, const double *urs, const double *urc, double *u_opt, int *k,      \
+                     int *e_flag, SOL *sol /* [B] or NULL */, const spcies_batch_opts *opts /* or NULL */,  \
+                     spcies_batch_info *info /* or NULL */)
+
 /* The solver families and the symbols each generated library exports (checked by tests/test_abi.py):
  *   SPCIES_CUDA_SOLVER(laxMPC_FISTA)       laxMPC_FISTA        laxMPC_FISTA_batch
  *   SPCIES_CUDA_SOLVER(laxMPC_ADMM)        laxMPC_ADMM         laxMPC_ADMM_batch
@@ -151,7 +163,7 @@ const char *spcies_cuda_last_error(void);
  *   SPCIES_CUDA_SOLVER(MPCT_EADMM)         MPCT_EADMM          MPCT_EADMM_batch
  *   SPCIES_CUDA_SOLVER(MPCT_ADMM_cs)       MPCT_ADMM_cs        MPCT_ADMM_cs_batch
  *   SPCIES_CUDA_SOLVER(MPCT_ADMM_semiband) MPCT_ADMM_semiband  MPCT_ADMM_semiband_batch
- *   SPCIES_CUDA_SOLVER(HMPC_ADMM)          HMPC_ADMM           HMPC_ADMM_batch   (ADMM, ADMM_split and SADMM_split)
+ *   SPCIES_CUDA_SOLVER(HMPC_ADMM)          HMPC_ADMM           HMPC_ADMM_batch   (ADMM, ADMM_split, SADMM_split; ellipHMPC: _6REF)
  */
 
 #ifdef __cplusplus

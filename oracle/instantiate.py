@@ -228,7 +228,8 @@ def build_reference(spec, save_name, cflags=('-O3',), force=False):
         with open(os.path.join(tmp, save_name + '.h'), 'w') as f:
             f.write(files['h'])
         has_r = 1 if 'r_ellip' in spec.extra_inputs else 0
-        cmd = ['gcc', *cflags, '-fPIC', '-shared', '-w', '-I', tmp,
+        nref = 3 if 'xrs' in spec.extra_inputs else 1
+        cmd = ['gcc', *cflags, '-fPIC', '-shared', '-w', '-I', tmp, f'-DSPCIES_NREF={nref}',
                f'-DSPCIES_HDR="{save_name}.h"', f'-DSPCIES_FUNC={spec.func_name}',
                f'-DSPCIES_SOL=sol_{save_name}', f'-DSPCIES_HAS_R={has_r}',
                os.path.join(tmp, save_name + '.c'), DRIVER_SRC, '-o', so_path, '-lm', '-lpthread']
@@ -274,6 +275,7 @@ class RefSolver:
             self.layout = [(str(a), int(b)) for a, b in json.load(f)]
         self.n, self.m = spec.dims['n'], spec.dims['m']
         self.has_r = 'r_ellip' in spec.extra_inputs
+        self.nref = 3 if 'xrs' in spec.extra_inputs else 1
         self.sol_len = sum(l for _, l in self.layout)
         self.lib.spcies_ref_sol_doubles.restype = ctypes.c_long
         assert self.lib.spcies_ref_sol_doubles() == self.sol_len, 'sol_<name> layout mismatch'
@@ -289,9 +291,15 @@ class RefSolver:
     def solve_batch(self, x0, xr, ur, r=None, threads=1, want_sol=False):
         """Loop of single-instance reference calls (in C).  Returns ``u [B,m], k [B], e [B]`` (+ sol dict)."""
         x0 = np.ascontiguousarray(np.atleast_2d(x0), dtype=np.float64)
+        B = x0.shape[0]
+        if self.nref == 3:      # xr = (x_re, x_rs, x_rc), ur = (u_re, u_rs, u_rc)
+            xs = [np.ascontiguousarray(np.atleast_2d(a), dtype=np.float64) for a in xr]
+            us = [np.ascontiguousarray(np.atleast_2d(a), dtype=np.float64) for a in ur]
+            assert all(a.shape == (B, self.n) for a in xs) and all(a.shape == (B, self.m) for a in us)
+            xr, ur = xs[0], us[0]
+            self.lib.spcies_ref_set_refs(self._p(xs[1]), self._p(xs[2]), self._p(us[1]), self._p(us[2]))
         xr = np.ascontiguousarray(np.atleast_2d(xr), dtype=np.float64)
         ur = np.ascontiguousarray(np.atleast_2d(ur), dtype=np.float64)
-        B = x0.shape[0]
         assert x0.shape == (B, self.n) and xr.shape == (B, self.n) and ur.shape == (B, self.m)
         if self.has_r:
             r = np.ascontiguousarray(np.broadcast_to(np.asarray(r, dtype=np.float64).ravel(), (B,)))
@@ -313,7 +321,11 @@ class RefSolver:
         return u, k, e, out
 
     def solve(self, x0, xr, ur, r=None):
-        u, k, e, sol = self.solve_batch(np.asarray(x0)[None], np.asarray(xr)[None], np.asarray(ur)[None],
+        if self.nref == 3:
+            xr, ur = [np.asarray(a)[None] for a in xr], [np.asarray(a)[None] for a in ur]
+        else:
+            xr, ur = np.asarray(xr)[None], np.asarray(ur)[None]
+        u, k, e, sol = self.solve_batch(np.asarray(x0)[None], xr, ur,
                                         r=None if r is None else np.asarray([r], dtype=float), want_sol=True)
         return u[0], int(k[0]), int(e[0]), {name: v[0] for name, v in sol.items()}
 

@@ -11,7 +11,11 @@
  *   SPCIES_FUNC  e.g. laxMPC_FISTA    the reference solver symbol
  *   SPCIES_SOL   sol_<save_name>
  *   SPCIES_HAS_R 0|1                  1 for ellipMPC_ADMM_soc (extra double *r_ellip input)
+ *   SPCIES_NREF  1|3                  3 for ellipHMPC (x_re, x_rs, x_rc, u_re, u_rs, u_rc; header_ellipHMPC_ADMM_C.h:24)
  */
+#ifndef SPCIES_NREF
+#define SPCIES_NREF 1
+#endif
 #include SPCIES_HDR
 #include <pthread.h>
 #include <stdlib.h>
@@ -20,6 +24,7 @@
 typedef struct {
     long lo, hi;
     const double *x0, *xr, *ur, *r;
+    const double *xr2, *xr3, *ur2, *ur3;
     double *u, *sol;
     int *k, *e;
 } slice_t;
@@ -37,7 +42,14 @@ static void *run_slice(void *arg) {
         memcpy(xr, s->xr + i * nn_, sizeof xr);
         memcpy(ur, s->ur + i * mm_, sizeof ur);
         memset(&sol, 0, sizeof sol);
-#if SPCIES_HAS_R
+#if SPCIES_NREF == 3
+        double xr2[nn_], xr3[nn_], ur2[mm_], ur3[mm_];
+        memcpy(xr2, s->xr2 + i * nn_, sizeof xr2);
+        memcpy(xr3, s->xr3 + i * nn_, sizeof xr3);
+        memcpy(ur2, s->ur2 + i * mm_, sizeof ur2);
+        memcpy(ur3, s->ur3 + i * mm_, sizeof ur3);
+        SPCIES_FUNC(x0, xr, xr2, xr3, ur, ur2, ur3, u, &k, &e, &sol);
+#elif SPCIES_HAS_R
         double r = s->r[i];
         SPCIES_FUNC(x0, xr, ur, &r, u, &k, &e, &sol);
 #else
@@ -49,6 +61,11 @@ static void *run_slice(void *arg) {
         if (s->sol) memcpy(s->sol + i * nsol, &sol, sizeof sol);
     }
     return NULL;
+}
+
+static const double *g_extra[4];   /* set by spcies_ref_set_refs() before spcies_ref_batch(): x_rs, x_rc, u_rs, u_rc */
+void spcies_ref_set_refs(const double *xr2, const double *xr3, const double *ur2, const double *ur3) {
+    g_extra[0] = xr2; g_extra[1] = xr3; g_extra[2] = ur2; g_extra[3] = ur3;
 }
 
 int spcies_ref_batch(long B, const double *x0, const double *xr, const double *ur, const double *r,
@@ -63,7 +80,7 @@ int spcies_ref_batch(long B, const double *x0, const double *xr, const double *u
         long lo = t * per, hi = lo + per;
         if (lo > B) lo = B;
         if (hi > B) hi = B;
-        sl[t] = (slice_t){lo, hi, x0, xr, ur, r, u, sol, k, e};
+        sl[t] = (slice_t){lo, hi, x0, xr, ur, r, g_extra[0], g_extra[1], g_extra[2], g_extra[3], u, sol, k, e};
     }
     if (nthreads == 1) { run_slice(&sl[0]); return 0; }
     for (int t = 0; t < nthreads; t++)

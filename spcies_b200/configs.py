@@ -55,6 +55,19 @@ def reference_test(name: str, N: int = 10, **solver_overrides):
         param = dict(Q=Q, R=R, T=10.0 * Q, S=R, N=N)
         so = dict(rho_base=2.0, rho_mult=20.0, k_max=5000, tol=1e-7)
         kw = dict(formulation='MPCT', method='ADMM', submethod='cs')
+    elif name in ('HMPC_ADMM', 'ellipHMPC_ADMM'):
+        # tests/test_HMPC_ADMM.m:6-22: method 'ADMM' with the default (empty) submethod = the non-split solver
+        param = dict(Q=Q, R=R, N=N, w=3 * 1.627 * 0.2, Te=10.0 * N * Q, Se=R)
+        param['Th'] = param['Te']
+        param['Sh'] = 0.5 * param['Se']
+        so = dict(rho=2.0, sigma=20.0, k_max=5000, tol_p=1e-7, tol_d=1e-7, use_soc=False)
+        kw = dict(formulation='HMPC' if name == 'HMPC_ADMM' else 'ellipHMPC', method='ADMM', submethod='')
+        if name == 'ellipHMPC_ADMM':
+            # coupled constraints y = E x + F u (the formulation needs them); here the box constraints written that way
+            n_, m_ = sys['n'], sys['m']
+            sys = dict(sys, E=np.vstack([np.eye(n_), np.zeros((m_, n_))]), F=np.vstack([np.zeros((n_, m_)), np.eye(m_)]),
+                       LBy=np.concatenate([sys['LBx'], sys['LBu']]), UBy=np.concatenate([sys['UBx'], sys['UBu']]))
+            so['sigma'] = 0.0
     elif name in ('HMPC_ADMM_split', 'HMPC_SADMM_split'):
         param = dict(Q=Q, R=R, N=N, w=3 * 1.627 * 0.2, Te=10.0 * N * Q, Se=R)
         param['Th'] = param['Te']

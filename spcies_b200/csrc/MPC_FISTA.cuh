@@ -716,6 +716,7 @@ __global__ void __launch_bounds__(BLOCK, 1) fista_kernel(const BatchIO io, const
 struct Traits {
     static constexpr int NN = n, MM = m, NMM = nm;
     static constexpr bool HAS_R = false;
+    static constexpr int NREF = 1;
     static constexpr bool HAS_VARB = true;
     static constexpr bool HAS_PARK = true;                   // phase-1 / phase-2 launches (park & resume the slow tail)
     static constexpr int PARK_DOUBLES = fista::PARK_DOUBLES;

@@ -155,6 +155,7 @@ __device__ __forceinline__ void stage_constants(void *smem_dst, const void *gmem
 struct BatchIO {
     long long B;
     const double *x0, *xr, *ur, *r;   // [B][nn_], [B][nn_], [B][mm_], [B] (r: solvers with r_ellip only)
+    const double *xr2, *xr3, *ur2, *ur3;   // solvers with three references (ellipHMPC: xr = x_re, xr2 = x_rs, xr3 = x_rc; same for ur), else nullptr
     const double *LB, *UB;            // optional per-instance bounds [B][nm_], or nullptr
     double *u;                        // [B][mm_]
     int *k, *e;                       // [B]

@@ -17,7 +17,7 @@ typedef Runtime<SPCIES_TRAITS> RT;
 // The reference's single-instance call = a batch of one.  Timing fields keep the reference's meaning and unit
 // (milliseconds, docs/timing.md:9-22): update_time = host->device, solve_time = kernel, polish_time = device->host.
 static inline void single_instance(double *x0_in, double *xr_in, double *ur_in, double *r_ellip, double *u_opt,
-                                   int *k_in, int *e_flag, SPCIES_SOL_T *sol) {
+                                   int *k_in, int *e_flag, SPCIES_SOL_T *sol, const double *const *extra = nullptr) {
     spcies_batch_info info;
 #ifdef DEBUG
     SPCIES_SOL_T tmp;
@@ -28,7 +28,7 @@ static inline void single_instance(double *x0_in, double *xr_in, double *ur_in, 
 #else
                            nullptr,
 #endif
-                           nullptr, &info);
+                           nullptr, &info, extra);
     if (rc != 0) {
         if (e_flag) *e_flag = SPCIES_CUDA_EFLAG_DEVICE;
         if (k_in) *k_in = 0;
@@ -86,7 +86,20 @@ int spcies_cuda_kernel_attributes(int arith, int *regs, int *smem_static, int *s
     return 0;
 }
 
-#if SPCIES_HAS_R
+#if defined(SPCIES_NREF) && SPCIES_NREF == 3
+// three references (x_re, x_rs, x_rc, u_re, u_rs, u_rc): header_ellipHMPC_ADMM_C.h:24
+void SPCIES_FUNC(double *x0_in, double *xre_in, double *xrs_in, double *xrc_in, double *ure_in, double *urs_in, double *urc_in,
+                 double *u_opt, int *k_in, int *e_flag, SPCIES_SOL_T *sol) {
+    const double *extra[4] = {xrs_in, xrc_in, urs_in, urc_in};
+    ::spcies::single_instance(x0_in, xre_in, ure_in, nullptr, u_opt, k_in, e_flag, sol, extra);
+}
+int SPCIES_CAT(SPCIES_FUNC, _batch)(long B, const double *x0, const double *xre, const double *xrs, const double *xrc,
+                                    const double *ure, const double *urs, const double *urc, double *u_opt, int *k, int *e_flag,
+                                    SPCIES_SOL_T *sol, const spcies_batch_opts *opts, spcies_batch_info *info) {
+    const double *extra[4] = {xrs, xrc, urs, urc};
+    return ::spcies::RT::get().run(B, x0, xre, ure, nullptr, u_opt, k, e_flag, reinterpret_cast<double *>(sol), opts, info, extra);
+}
+#elif SPCIES_HAS_R
 void SPCIES_FUNC(double *x0_in, double *xr_in, double *ur_in, double *r_ellip, double *u_opt, int *k_in, int *e_flag,
                  SPCIES_SOL_T *sol) {
     ::spcies::single_instance(x0_in, xr_in, ur_in, r_ellip, u_opt, k_in, e_flag, sol);

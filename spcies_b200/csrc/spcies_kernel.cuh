@@ -115,6 +115,11 @@ template <class S> struct PolicyTraits {
     typedef typename S::real real;
     static constexpr int NN = nn_, MM = mm_, NMM = nm_;
     static constexpr bool HAS_R = (SPCIES_HAS_R != 0);
+#ifdef SPCIES_NREF
+    static constexpr int NREF = SPCIES_NREF;
+#else
+    static constexpr int NREF = 1;
+#endif
     static constexpr bool HAS_VARB = S::HAS_VARB;
     static constexpr int SOL_DOUBLES = (int)(sizeof(SPCIES_SOL_T) / sizeof(double));
     typedef spcies_consts Consts;

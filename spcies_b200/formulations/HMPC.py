@@ -108,7 +108,7 @@ def compute_HMPC_ADMM_split_ingredients(recipe, box_constraints=True):
         d = dsoc
     n_s = C.shape[0]
 
-    sigma, rho = float(solver['sigma']), float(solver['rho'])
+    sigma, rho = float(solver['sigma']) or 1.0, float(solver['rho'])      # (ellipHMPC reuses the blocks with its sigma = 0)
     Hh = sla.block_diag(H + sigma * np.eye(dim), rho * np.eye(n_s))
     Gh = np.block([[G, np.zeros((n_eq, n_s))], [C, np.eye(n_s)]])
     bh = np.concatenate([b, d])
@@ -195,3 +195,141 @@ def cons_HMPC_ADMM_split(recipe):
 
 def cons_HMPC_SADMM_split(recipe):
     return _cons_split(recipe, True)
+
+
+# --------------------------------------------------------------------------------------
+# ADMM without the (z_hat, s_hat) splitting: HMPC / ADMM / '' (the toolbox default for HMPC,
+# classes/Spcies_options.m:94,104) and ellipHMPC / ADMM
+# --------------------------------------------------------------------------------------
+def compute_HMPC_ADMM_ingredients(recipe, box_constraints=True, ellip=False):
+    """formulations/+HMPC/compute_HMPC_ADMM_ingredients.m:25-332 and compute_ellipHMPC_ADMM_ingredients.m:25-288.
+
+    Same Hessian / equality blocks as the split solver; the constraints enter through ``s = -(C z [- d])`` with
+    ``C = blkdiag(box part, cone part)``, ``Hh = H + rho C'C``, ``M1 = Hh^-1 G' W^-1 G Hh^-1 - Hh^-1``,
+    ``M2 = Hh^-1 G' W^-1`` (first n columns).  MATLAB's pivoted ``ldl`` of the KKT matrix (:246-253) only feeds the
+    ``sparse`` variant, which the C template of this solver does not have."""
+    from .. import sp_utils
+    base = compute_HMPC_ADMM_split_ingredients(recipe, box_constraints and not ellip)
+    A, B, n, m, N = get_sys_param(recipe)
+    sys, param, solver = recipe.sys, recipe.param, recipe.options.solver
+    nm = n + m
+    H, G, dim, n_eq = base['H'], base['G'], base['dim'], base['n_eq']
+    E, F, LBy, UBy = base['E'], base['F'], base['LBy'], base['UBy']
+    n_y = LBy.size
+    use_soc = bool(solver.get('use_soc', False))
+    box = box_constraints and not ellip
+
+    if use_soc:
+        C_aux, dsoc = [], []
+        for j in range(n_y):
+            Ej, Fj = E[j:j + 1, :], F[j:j + 1, :]
+            Eub, Elb = sla.block_diag(Ej, -Ej, -Ej), sla.block_diag(-Ej, -Ej, -Ej)
+            Fub, Flb = sla.block_diag(Fj, -Fj, -Fj), sla.block_diag(-Fj, -Fj, -Fj)
+            C_aux.append(np.vstack([np.hstack([Eub, Fub]), np.hstack([Elb, Flb])]))
+            dsoc += [UBy[j], 0.0, 0.0, -LBy[j], 0.0, 0.0]
+        C_aux, dsoc, n_soc = np.vstack(C_aux), np.array(dsoc), 2 * n_y
+    elif box:
+        C_n = np.vstack([np.kron(np.eye(3), -np.eye(n)[j:j + 1, :]) for j in range(n)])
+        C_m = np.vstack([np.kron(np.eye(3), -np.eye(m)[j:j + 1, :]) for j in range(m)])
+        C_aux, dsoc, n_soc = sla.block_diag(C_n, C_m), np.zeros(3 * n_y), n_y
+    else:
+        C_aux = np.vstack([np.hstack([np.kron(np.eye(3), -E[j:j + 1, :]), np.kron(np.eye(3), -F[j:j + 1, :])])
+                           for j in range(n_y)])
+        dsoc, n_soc = np.zeros(3 * n_y), n_y
+    if box:
+        C = sla.block_diag(-np.eye(m), np.kron(np.eye(N - 1), sla.block_diag(-np.eye(n), -np.eye(m))), C_aux)
+        d = np.concatenate([np.zeros((N - 1) * nm + m), dsoc])
+        LB, UB = base['LB'], base['UB']
+        n_box = (N - 1) * nm + m
+    else:
+        C = sla.block_diag(-F, np.kron(np.eye(N - 1), np.hstack([-E, -F])), C_aux)
+        d = np.concatenate([np.zeros(N * n_y), dsoc])
+        LB, UB = np.kron(np.ones(N), LBy), np.kron(np.ones(N), UBy)
+        n_box = N * n_y
+    n_s = C.shape[0]
+    rho = float(solver['rho'])
+    Hh = H + rho * (C.T @ C)
+    Hhi = np.linalg.inv(Hh)
+    W = G @ Hhi @ G.T
+    Wi = np.linalg.inv(W)
+    M1 = Hhi @ G.T @ Wi @ G @ Hhi - Hhi
+    M2 = (Hhi @ G.T @ Wi)[:, :n].copy()
+    v = dict(base)
+    v.update(dim=dim, n_s=n_s, n_eq=n_eq, n_y=n_y, n_soc=n_soc, n_box=n_box, C=C, d=d, LB=LB, UB=UB, Hh=Hh, M1=M1, M2=M2,
+             C_CSR=sp_utils.full2CSR(C), Ct_CSR=sp_utils.full2CSR(C.T), rho=rho, rho_i=1.0 / rho, use_soc=use_soc,
+             box_constraints=box, R=np.asarray(param['R'], float), Th=np.asarray(param['Th'], float),
+             Sh=np.asarray(param['Sh'], float))
+    if ellip:                                   # compute_ellipHMPC_ADMM_ingredients.m:222-223 (sic: tightened by sigma)
+        sg = float(solver.get('sigma', 0.0))
+        v['LBy'], v['UBy'] = LBy + sg, UBy - sg
+    return v
+
+
+def _cons_nonsplit(recipe, ellip: bool) -> SolverSpec:
+    opts = recipe.options
+    solver = opts.solver
+    box = solver.get('box_constraints', None)
+    if box is None or (isinstance(box, (list, tuple)) and len(box) == 0):
+        box = 'E' not in recipe.sys                     # cons_HMPC_ADMM_C.m:57-63
+    box = bool(box) and not ellip
+    v = compute_HMPC_ADMM_ingredients(recipe, box, ellip)
+    n, m, N, dim, n_s, n_eq = v['n'], v['m'], v['N'], v['dim'], v['n_s'], v['n_eq']
+    vopt = var_options(opts)
+    vopt_pen = var_options(opts, array=False)
+    prec = opts.precision
+    D = ('define',)
+    defs = default_defines(opts)
+    defs += [Row('nn_', n, True, 'uint', D), Row('mm_', m, True, 'uint', D), Row('nm_', n + m, True, 'uint', D),
+             Row('NN_', N, True, 'uint', D), Row('dim', dim, True, 'uint', D), Row('n_s', n_s, True, 'uint', D),
+             Row('n_eq', n_eq, True, 'uint', D), Row('n_soc', v['n_soc'], True, 'uint', D),
+             Row('n_y', v['n_y'], True, 'uint', D), Row('n_box', v['n_box'], True, 'uint', D),
+             Row('nrow_C', v['C_CSR'].nrow, True, 'uint', D), Row('nrow_Ct', v['Ct_CSR'].nrow, True, 'uint', D),
+             Row('k_max', int(solver['k_max']), True, 'uint', D),
+             Row('tol_p', float(solver['tol_p']), True, prec, D), Row('tol_d', float(solver['tol_d']), True, prec, D)]
+    if opts.method == 'SADMM':
+        defs += [Row('alpha_SADMM', float(solver['alpha']), True, prec, D), Row('IS_SYMMETRIC', 1, True, prec, D)]
+    if v['use_soc']:
+        defs.append(Row('USE_SOC', 1, True, prec, D))
+    consts = [Row('rho', v['rho'], True, prec, vopt_pen), Row('rho_i', v['rho_i'], True, prec, vopt_pen),
+              Row('A', v['A'], True, prec, vopt)]
+    for nm_ in ('C', 'Ct'):
+        s = v[nm_ + '_CSR']
+        consts += [Row(nm_ + '_val', s.val, True, prec, vopt), Row(nm_ + '_col', s.col, True, 'int', vopt),
+                   Row(nm_ + '_row', s.row, True, 'int', vopt)]
+    consts += [Row('QQ', v['Q'], True, prec, vopt), Row('Te', v['Te'], True, prec, vopt)]
+    if ellip:
+        consts.append(Row('Th', v['Th'], True, prec, vopt))
+    consts.append(Row('Se', v['Se'], True, prec, vopt))
+    if ellip:
+        consts.append(Row('Sh', v['Sh'], True, prec, vopt))
+    consts += [Row('LB', v['LB'], True, prec, vopt), Row('UB', v['UB'], True, prec, vopt),
+               Row('LBy', v['LBy'], True, prec, vopt), Row('UBy', v['UBy'], True, prec, vopt)]
+    if v['use_soc']:
+        consts.append(Row('d', v['d'], True, prec, vopt))
+    consts += [Row('M1', v['M1'], True, prec, vopt), Row('M2', v['M2'], True, prec, vopt)]
+    if opts.in_engineering:
+        consts += engineering_rows(v, prec, vopt)
+    if ellip:
+        return SolverSpec(
+            formulation='ellipHMPC', method='ADMM', submethod='', func_name='HMPC_ADMM', kernel='ellipHMPC_ADMM',
+            defines=defs, constants=consts,
+            ref_code='formulations/+HMPC/code_ellipHMPC_ADMM_C.c',
+            ref_header='formulations/+HMPC/header_ellipHMPC_ADMM_C.h',
+            extra_inputs=('xrs', 'xrc', 'urs', 'urc'),
+            sol_fields=(('z', dim), ('s', n_s), ('lambda', n_s)),
+            vars=v, dims=dict(n=n, m=m, N=N, dim=dim, n_s=n_s, n_eq=n_eq))
+    return SolverSpec(
+        formulation='HMPC', method=opts.method, submethod='', func_name='HMPC_ADMM', kernel='HMPC_ADMM',
+        defines=defs, constants=consts,
+        ref_code='formulations/+HMPC/code_HMPC_ADMM_C.c',
+        ref_header='formulations/+HMPC/header_HMPC_ADMM_C.h',
+        sol_fields=(('z', dim), ('s', n_s), ('lambda', n_s)),
+        vars=v, dims=dict(n=n, m=m, N=N, dim=dim, n_s=n_s, n_eq=n_eq))
+
+
+def cons_HMPC_ADMM(recipe):
+    return _cons_nonsplit(recipe, False)
+
+
+def cons_ellipHMPC_ADMM(recipe):
+    return _cons_nonsplit(recipe, True)

@@ -17,6 +17,8 @@ CONSTRUCTORS = {
     'ellipMPC_ADMM_soc': ellipMPC.cons_ellipMPC_ADMM_soc,
     'MPCT_EADMM': MPCT.cons_MPCT_EADMM,
     'MPCT_ADMM_cs': MPCT.cons_MPCT_ADMM_cs,
+    'HMPC_ADMM': HMPC.cons_HMPC_ADMM,
+    'ellipHMPC_ADMM': HMPC.cons_ellipHMPC_ADMM,
     'HMPC_ADMM_split': HMPC.cons_HMPC_ADMM_split,
     'HMPC_SADMM_split': HMPC.cons_HMPC_SADMM_split,
 }

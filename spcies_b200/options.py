@@ -30,7 +30,9 @@ LIST_ACCEPTED_SUBMETHODS = {
     'equMPC': {'ADMM': [''], 'FISTA': ['']},
     'ellipMPC': {'ADMM': ['', 'soc']},
     'MPCT': {'ADMM': ['cs', 'semiband'], 'EADMM': ['']},
-    'HMPC': {'ADMM': ['cs', 'split'], 'SADMM': ['split']},
+    # the reference lists {'cs', 'split'} for HMPC / ADMM (Spcies_options.m:84) but defaults to '' (:104) = cons_HMPC_ADMM_C.m,
+    # the non-split solver: the default is accepted here
+    'HMPC': {'ADMM': ['', 'cs', 'split'], 'SADMM': ['split']},
     'ellipHMPC': {'ADMM': ['']},
 }
 LIST_DEF_METHODS = {'laxMPC': 'ADMM', 'equMPC': 'ADMM', 'ellipMPC': 'ADMM',

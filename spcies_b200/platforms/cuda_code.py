@@ -44,6 +44,8 @@ KERNELS = {
     'MPCT_EADMM': ('MPCT_EADMM.cuh', {}),
     'MPCT_ADMM_cs': ('MPCT_ADMM_cs.cuh', {}),
     'HMPC_ADMM_split': ('HMPC_ADMM_split.cuh', {}),
+    'HMPC_ADMM': ('HMPC_ADMM.cuh', {'SPCIES_NREF': 1}),
+    'ellipHMPC_ADMM': ('HMPC_ADMM.cuh', {'SPCIES_NREF': 3}),
 }
 
 
@@ -116,6 +118,8 @@ def emit_text(spec, save_name):
           '    double run_time; // whole call (ms)',
           '} ' + sol_t + ';', '', '#ifdef __cplusplus', 'extern "C" {', '#endif']
     macro = 'SPCIES_CUDA_DECLARE_SOLVER_R' if has_r else 'SPCIES_CUDA_DECLARE_SOLVER'
+    if 'xrs' in spec.extra_inputs:
+        macro = 'SPCIES_CUDA_DECLARE_SOLVER_6REF'
     h += [f'{macro}({spec.func_name}, {sol_t});', '#ifdef __cplusplus', '}', '#endif', '', '#endif', '',
           '// This code is generated by the CUDA platform of spcies_b200 for the Spcies toolbox: '
           'https://github.com/GepocUS/Spcies', '']

@@ -68,6 +68,8 @@ class CudaSolver:
         self.sol_doubles = int(L.spcies_cuda_sol_doubles())
         self.func_name = spec.func_name if spec is not None else self._guess_func()
         self.has_r = hasattr(L, 'ellipMPC_ADMM_soc')
+        # three references (x_re, x_rs, x_rc) / (u_re, u_rs, u_rc): ellipHMPC, header_ellipHMPC_ADMM_C.h:24
+        self.nref = 3 if (spec is not None and 'xrs' in spec.extra_inputs) else 1
         self._single = getattr(L, self.func_name)
         self._single.restype = None
         self._batch = getattr(L, self.func_name + '_batch')
@@ -112,16 +114,19 @@ class CudaSolver:
     def solve(self, x0, xr, ur, r=None):
         """Single instance through the reference's own symbol and signature."""
         x0 = np.ascontiguousarray(x0, dtype=np.float64).ravel().copy()
-        xr = np.ascontiguousarray(xr, dtype=np.float64).ravel().copy()
-        ur = np.ascontiguousarray(ur, dtype=np.float64).ravel().copy()
-        if x0.size != self.n or xr.size != self.n or ur.size != self.m:
+        xrs = [np.ascontiguousarray(a, dtype=np.float64).ravel().copy() for a in (xr if self.nref == 3 else [xr])]
+        urs = [np.ascontiguousarray(a, dtype=np.float64).ravel().copy() for a in (ur if self.nref == 3 else [ur])]
+        if x0.size != self.n or len(xrs) != self.nref or len(urs) != self.nref or any(a.size != self.n for a in xrs) or \
+                any(a.size != self.m for a in urs):
             raise ValueError('x0 / xr / ur have the wrong dimensions')       # Spcies:<F>:nrhs / size checks of the MEX layer
         u = np.zeros(self.m)
         k, e = c_int(0), c_int(0)
         sol = np.zeros(self.sol_doubles)
-        args = [_dptr(x0), _dptr(xr), _dptr(ur)]
+        args = [_dptr(x0)] + [_dptr(a) for a in xrs] + [_dptr(a) for a in urs]
         if self.has_r:
-            rr = np.array([float(0.0 if r is None else r)])
+            if r is None:
+                raise ValueError('this solver takes the size of the terminal ellipsoid: r is required')
+            rr = np.array([float(r)])
             args.append(_dptr(rr))
         args += [_dptr(u), ctypes.byref(k), ctypes.byref(e), _dptr(sol)]
         self._single(*args)
@@ -133,17 +138,23 @@ class CudaSolver:
                     want_sol=False, out=None, block_threads=0, grid_blocks=0, tail_mode=0, tail_grace=0, engine=0, tail_caps=()):
         """B instances through ``<func>_batch``.  Arrays are ``[B, n]`` / ``[B, m]`` (instance-major)."""
         x0 = np.ascontiguousarray(x0, dtype=np.float64)
-        xr = np.ascontiguousarray(xr, dtype=np.float64)
-        ur = np.ascontiguousarray(ur, dtype=np.float64)
+        xrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (xr if self.nref == 3 else [xr])]
+        urs = [np.ascontiguousarray(a, dtype=np.float64) for a in (ur if self.nref == 3 else [ur])]
         B = x0.shape[0] if x0.ndim == 2 else 0
-        if x0.shape != (B, self.n) or xr.shape != (B, self.n) or ur.shape != (B, self.m):
+        if x0.shape != (B, self.n) or len(xrs) != self.nref or len(urs) != self.nref or \
+                any(a.shape != (B, self.n) for a in xrs) or any(a.shape != (B, self.m) for a in urs):
             raise ValueError('x0 / xr / ur must be [B, nn_], [B, nn_], [B, mm_]')
+        if self.has_r and r is None:
+            raise ValueError('this solver takes the size of the terminal ellipsoid: r [B] is required')
         if out is None:
             u = np.empty((B, self.m))
             k = np.empty(B, dtype=np.int32)
             e = np.empty(B, dtype=np.int32)
         else:
             u, k, e = out
+            for a, dt, shp in ((u, np.float64, (B, self.m)), (k, np.int32, (B,)), (e, np.int32, (B,))):
+                if not isinstance(a, np.ndarray) or a.dtype != dt or a.shape != shp or not a.flags['C_CONTIGUOUS']:
+                    raise ValueError('out = (u float64 [B, mm_], k int32 [B], e_flag int32 [B]), C-contiguous')
         sol = np.zeros((B, self.sol_doubles)) if want_sol else None
         opts = BatchOpts()
         opts.device, opts.n_devices, opts.arith = int(device), int(n_devices), int(arith)
@@ -161,7 +172,7 @@ class CudaSolver:
             opts.LB, opts.UB = LB.ctypes.data, UB.ctypes.data
             keep += [LB, UB]
         info = BatchInfo()
-        args = [c_long(B), _dptr(x0), _dptr(xr), _dptr(ur)]
+        args = [c_long(B), _dptr(x0)] + [_dptr(a) for a in xrs] + [_dptr(a) for a in urs]
         if self.has_r:
             rr = np.ascontiguousarray(np.broadcast_to(np.asarray(r, dtype=np.float64).ravel(), (B,)))
             keep.append(rr)

@@ -12,7 +12,30 @@ from spcies_b200.solver import ARITH_EXACT, ARITH_FAST, ENGINE_MMA, ENGINE_SCALA
 pytestmark = pytest.mark.gpu
 
 # solver -> (golden vector of the reference's own test, sol field) or None
-SOLVERS = {'T_MPCT_ADMM_cs': ('MPCT_ADMM', 'z')}
+SOLVERS = {'T_MPCT_ADMM_cs': ('MPCT_ADMM', 'z'), 'T_HMPC_ADMM': None, 'T_ellipHMPC_ADMM': None}
+
+
+def _inputs(sol, cfg, B, seed):
+    """(x0, xr, ur) of a synthetic batch; solvers with three references (ellipHMPC) get small harmonic components."""
+    b = sysmodel.synthetic_batch(cfg['sys'], B, seed=seed)
+    if sol.nref == 1:
+        return b['x0'], b['xr'], b['ur']
+    rng = np.random.default_rng(seed + 7)
+    n, m = sol.n, sol.m
+    xr = (b['xr'], rng.uniform(-0.02, 0.02, (B, n)), rng.uniform(-0.02, 0.02, (B, n)))
+    ur = (b['ur'], rng.uniform(-0.05, 0.05, (B, m)), rng.uniform(-0.05, 0.05, (B, m)))
+    return b['x0'], xr, ur
+
+
+def _cut(a, sl):
+    return tuple(x[sl] for x in a) if isinstance(a, tuple) else a[sl]
+
+
+def _status(sol, cfg):
+    st = cfg['status']
+    if sol.nref == 1:
+        return st['x'], st['xr'], st['ur']
+    return st['x'], (st['xr'], 0.01 * np.ones(sol.n), np.zeros(sol.n)), (st['ur'], np.zeros(sol.m), 0.02 * np.ones(sol.m))
 
 
 def _ref(name):
@@ -23,9 +46,9 @@ def _ref(name):
 @pytest.mark.parametrize('name', list(SOLVERS))
 def test_single_instance_vs_golden(name, golden):
     sol, spec, cfg = prebuilt.get(name)
-    st = cfg['status']
-    u, k, e, s = sol.solve(st['x'], st['xr'], st['ur'])
-    ur_, kr, er, sr = _ref(name).solve(st['x'], st['xr'], st['ur'])
+    x, xr, ur = _status(sol, cfg)
+    u, k, e, s = sol.solve(x, xr, ur)
+    ur_, kr, er, sr = _ref(name).solve(x, xr, ur)
     assert e == er == 1 and abs(k - kr) <= 1
     if SOLVERS[name] is not None:
         gold_name, field = SOLVERS[name]
@@ -39,9 +62,9 @@ def test_single_instance_vs_golden(name, golden):
 @pytest.mark.parametrize('name', list(SOLVERS))
 def test_exact_mode_bit_identical_with_debug_payload(name):
     sol, spec, cfg = prebuilt.get(name)
-    batch = sysmodel.synthetic_batch(cfg['sys'], 300, seed=31)
-    u, k, e, info, s = sol.solve_batch(batch['x0'], batch['xr'], batch['ur'], arith=ARITH_EXACT, want_sol=True)
-    ur_, kr, er, sr = _ref(name).solve_batch(batch['x0'], batch['xr'], batch['ur'], want_sol=True, threads=8)
+    x0, xr, ur = _inputs(sol, cfg, 300, 31)
+    u, k, e, info, s = sol.solve_batch(x0, xr, ur, arith=ARITH_EXACT, want_sol=True)
+    ur_, kr, er, sr = _ref(name).solve_batch(x0, xr, ur, want_sol=True, threads=8)
     assert np.array_equal(k, kr) and np.array_equal(e, er)
     assert np.array_equal(u.view(np.uint64), ur_.view(np.uint64))
     for f, _len in spec.sol_fields:
@@ -53,14 +76,15 @@ def test_exact_mode_bit_identical_with_debug_payload(name):
 def test_dense_engine_parity(name):
     sol, spec, cfg = prebuilt.get(name)
     B = 3000
-    batch = sysmodel.synthetic_batch(cfg['sys'], B, seed=32)
-    ur_, kr, er = _ref(name).solve_batch(batch['x0'], batch['xr'], batch['ur'], threads=16)
-    u, k, e, info = sol.solve_batch(batch['x0'], batch['xr'], batch['ur'], arith=ARITH_FAST, engine=ENGINE_MMA)
+    x0, xr, ur = _inputs(sol, cfg, B, 32)
+    ur_, kr, er = _ref(name).solve_batch(x0, xr, ur, threads=16)
+    u, k, e, info = sol.solve_batch(x0, xr, ur, arith=ARITH_FAST, engine=ENGINE_MMA)
     gate(spec, u, k, e, ur_, kr, er)
     assert info['sum_k'] == int(k.sum()) and info['n_not_converged'] == int((e == -1).sum())
-    u2, k2, e2, _ = sol.solve_batch(batch['x0'][:256], batch['xr'][:256], batch['ur'][:256], arith=ARITH_FAST, engine=ENGINE_SCALAR)
+    sl = slice(0, 256)
+    u2, k2, e2, _ = sol.solve_batch(x0[sl], _cut(xr, sl), _cut(ur, sl), arith=ARITH_FAST, engine=ENGINE_SCALAR)
     gate(spec, u2, k2, e2, ur_[:256], kr[:256], er[:256])
-    u3, k3, e3, _ = sol.solve_batch(batch['x0'], batch['xr'], batch['ur'])                   # default engine = the dense engine
+    u3, k3, e3, _ = sol.solve_batch(x0, xr, ur)                                              # default engine = the dense engine
     assert np.array_equal(u3.view(np.uint64), u.view(np.uint64)) and np.array_equal(k3, k) and np.array_equal(e3, e)
 
 
@@ -68,17 +92,17 @@ def test_dense_engine_parity(name):
 def test_dense_engine_ragged_batches(name):
     sol, spec, cfg = prebuilt.get(name)
     for B in (1, 7, 8, 9, 47, 49, 65, 130, 700):
-        batch = sysmodel.synthetic_batch(cfg['sys'], B, seed=33 + B)
-        u, k, e, info = sol.solve_batch(batch['x0'], batch['xr'], batch['ur'], engine=ENGINE_MMA)
-        ur_, kr, er = _ref(name).solve_batch(batch['x0'], batch['xr'], batch['ur'], threads=8)
+        x0, xr, ur = _inputs(sol, cfg, B, 33 + B)
+        u, k, e, info = sol.solve_batch(x0, xr, ur, engine=ENGINE_MMA)
+        ur_, kr, er = _ref(name).solve_batch(x0, xr, ur, threads=8)
         gate(spec, u, k, e, ur_, kr, er)
 
 
 @pytest.mark.parametrize('name', list(SOLVERS))
 def test_dense_engine_refused_where_it_cannot_run(name):
     sol, spec, cfg = prebuilt.get(name)
-    batch = sysmodel.synthetic_batch(cfg['sys'], 16, seed=34)
+    x0, xr, ur = _inputs(sol, cfg, 16, 34)
     with pytest.raises(SpciesCudaError):
-        sol.solve_batch(batch['x0'], batch['xr'], batch['ur'], arith=ARITH_EXACT, engine=ENGINE_MMA)
+        sol.solve_batch(x0, xr, ur, arith=ARITH_EXACT, engine=ENGINE_MMA)
     with pytest.raises(SpciesCudaError):
-        sol.solve_batch(batch['x0'], batch['xr'], batch['ur'], engine=ENGINE_MMA, want_sol=True)
+        sol.solve_batch(x0, xr, ur, engine=ENGINE_MMA, want_sol=True)

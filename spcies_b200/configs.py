@@ -26,8 +26,8 @@ def _T_sumP(sys, Q, R):
     return np.diag(P.sum(axis=1))
 
 
-def reference_test(name: str, N: int = 10, **solver_overrides):
-    sys = sysmodel.oscillating_masses_sys()
+def reference_test(name: str, N: int = 10, masses: int = 3, forces=None, **solver_overrides):
+    sys = sysmodel.oscillating_masses_sys(p=masses, F=forces)
     Q, R = _QR(sys)
     st = sysmodel.tester_status(sys)
     if name in ('laxMPC_FISTA', 'laxMPC_ADMM'):
@@ -93,6 +93,9 @@ def bench_config(name: str):
         'C4': ('ellipMPC_ADMM_soc', 10, dict(rho=15.0, sigma=10.0, tol_p=1e-4, tol_d=1e-4, k_max=1000)),
         'C5a': ('HMPC_SADMM_split', 50, dict(rho=2.0, sigma=20.0, alpha=0.95, tol_p=1e-4, tol_d=1e-4, k_max=1000)),
         'C5b': ('MPCT_EADMM', 50, dict(rho_base=2.0, rho_mult=20.0, tol=1e-4, k_max=1000)),
+        # round-2 solvers at the reference tests' problem, default tolerances (rho: the penalty that converges in O(100) iterations)
+        'C6': ('MPCT_ADMM_cs', 10, dict(rho=2.0, tol=1e-4, k_max=1000)),
+        'C7': ('HMPC_ADMM', 10, dict(rho=2.0, tol_p=1e-4, tol_d=1e-4, k_max=1000)),
     }
     solver, N, so = table[name]
     cfg = reference_test(solver, N=N, **so)

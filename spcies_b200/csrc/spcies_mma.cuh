@@ -32,7 +32,9 @@ __device__ __forceinline__ void mv(double (&out)[2], const double2 M, const doub
 }
 
 template <int n, int m> struct MmaLayout {
-    static_assert(n >= 5 && n <= 6 && n + m <= 8, "MmaLayout: 5 <= nn_ <= 6, nn_ + mm_ <= 8");
+    // the layout exists for 5 <= nn_ <= 6, nn_ + mm_ <= 8; the engines test OK (their MMA_SHAPE_OK) before they are used -- for any
+    // other system the tables are compiled but never filled or read, and the solver runs on its one-thread-per-instance kernel
+    static constexpr bool OK = n >= 5 && n <= 6 && n + m <= 8;
     __host__ __device__ static constexpr int col_x(int e) { return e < 4 ? 2 * e : 2 * (e - 4) + 1; }
     __host__ __device__ static constexpr int col_u(int j) { return 2 * (n - 4 + j) + 1; }
     __host__ __device__ static constexpr int col_dup(int e) { return 2 * (e - 4 + 2) + 1; }   // second copy of x_e, e >= 4

@@ -57,15 +57,17 @@ def dlqr(A, B, Q, R):
     return K, P
 
 
-def oscillating_masses_sys(Ts: float = 0.2):
-    """The 3-mass system of tests/spcies_tester.m:90-111 (== example_OscMass.m:17-36).
+def oscillating_masses_sys(Ts: float = 0.2, p: int = 3, F=None):
+    """The 3-mass system of tests/spcies_tester.m:90-111 (== example_OscMass.m:17-36); ``p`` / ``F`` select another chain of
+    +sp_utils/gen_oscillating_masses.m:28-59 (``p`` masses, forces on the masses flagged in ``F``; default: first and last),
+    with the same masses / springs / bounds pattern -- the systems of other dimensions used by the shape tests.
 
     Returns a ``sys`` dict with the reference's field names.
     """
-    p = 3
-    M = [1.0, 0.5, 1.0]
+    M = [1.0, 0.5, 1.0] if p == 3 else [1.0 if i % 2 == 0 else 0.5 for i in range(p)]
     K = 2.0 * np.ones(p + 1)
-    F = [1, 0, 1]
+    if F is None:
+        F = [1, 0, 1] if p == 3 else [1] + [0] * (p - 2) + [1]
     Ac, Bc = gen_oscillating_masses(M, K, F)
     A, B = c2d_zoh(Ac, Bc, Ts)
     n, m = B.shape

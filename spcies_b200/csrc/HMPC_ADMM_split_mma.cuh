@@ -298,10 +298,10 @@ __global__ void __launch_bounds__(MMA_BLOCK, 1) hmpc_mma_kernel(const BatchIO io
                 for (int b = 0; b < NBZ; ++b) update_z(t + b, acc[b]);
             }
             // the remaining ZT % NBZ tiles of z in one pass of their own (a single-tile pass would be a 2 NIN-deep dependent chain)
-            constexpr int REM = ZT % NBZ;
+            constexpr int REM = ZT % NBZ, REMD = REM > 0 ? REM : 1;   // (this kernel is not a template: the branch is compiled for REM = 0 too)
             if constexpr (REM > 0) {
-                double acc[REM][2];
-                hmpc_product<REM, PFZ>(frag + ((size_t)t * NIN) * 32 + lane, st + BLK_QH * 32, ring, acc);
+                double acc[REMD][2];
+                hmpc_product<REMD, PFZ>(frag + ((size_t)t * NIN) * 32 + lane, st + BLK_QH * 32, ring, acc);
 #pragma unroll
                 for (int b = 0; b < REM; ++b) update_z(t + b, acc[b]);
             }

@@ -48,7 +48,7 @@
 extern "C" {
 #endif
 
-#define SPCIES_CUDA_ABI_VERSION 1
+#define SPCIES_CUDA_ABI_VERSION 2   /* 2: closed-loop entry points; spcies_batch_opts.warm_start / .plant_AB */
 
 /* infrastructure error codes (positive values below 1000 are cudaError_t) */
 #define SPCIES_CUDA_EINVAL      1001   /* bad argument (NULL buffer, B < 0, ...) */
@@ -93,7 +93,11 @@ typedef struct {
     int tail_grace;          /* iterations an instance may still run after the queue ran dry before it is parked (0: 32) */
     int engine;              /* SPCIES_CUDA_ENGINE_AUTO (default) | _SCALAR | _MMA, see above */
     int tail_caps[3];        /* increasing iteration caps of SPCIES_CUDA_TAIL_CAPS, 0-terminated (all 0: 96, 320) */
-    int reserved[2];
+    int warm_start;          /* closed loop: 0 = cold start; 1 = start every sampling time from the dual point of the previous one  */
+                             /*   (FISTA solvers: the `lambda` argument of platforms/Matlab/spcies_laxMPC_FISTA_solver.m:161-164);  */
+                             /*   2 = the same, shifted by one stage (the horizon receded: lambda_l <- lambda_{l+1})                */
+    int reserved[1];
+    const double *plant_AB;  /* closed loop: plant x+ = [A B] (x; u) as a row-major [nn_][nm_] HOST array; NULL: the prediction model */
 } spcies_batch_opts;
 
 /* Measurements of the last batched call (all device times from CUDA events on the launching stream). */
@@ -126,6 +130,13 @@ int         spcies_cuda_kernel_attributes(int arith, int *regs, int *smem_static
 void        spcies_cuda_free(void);            /* release device buffers, streams and events              */
 const char *spcies_cuda_last_error(void);
 
+/* ---- closed loop (new) -----------------------------------------------------------------------------
+ * `<func>_closed_loop` simulates `steps` sampling times of the closed loop  u_t = MPC(x_t),  x_{t+1} = A x_t + B u_t  for B
+ * independent instances (the loop of examples/cl_in_C/main_cl_in_C.c:100-117, batched), with constant references.  The state
+ * never returns to the host between sampling times; the FISTA tensor-core engine keeps every instance on chip for the whole
+ * run (the successor state is one more MMA), the other solvers launch once per sampling time on device-resident arrays.
+ *   x_traj [steps + 1][B][nn_] (x_traj[0] = x0; may be NULL), u_traj [steps][B][mm_], k_traj / e_traj [steps][B]. */
+
 /* ---- per-solver entry points ----------------------------------------------------------------------
  * Written as macros because the `sol_<save_name>` type is generated; `<save_name>.h` expands them.
  * NAME is the reference function name, SOL the generated `sol_<save_name>` type.                      */
@@ -133,7 +144,10 @@ const char *spcies_cuda_last_error(void);
     void NAME(double *x0_in, double *xr_in, double *ur_in, double *u_opt, int *k_in, int *e_flag, SOL *sol); \
     int NAME##_batch(long B, const double *x0, const double *xr, const double *ur,                         \
                      double *u_opt, int *k, int *e_flag, SOL *sol /* [B] or NULL */,                       \
-                     const spcies_batch_opts *opts /* or NULL */, spcies_batch_info *info /* or NULL */)
+                     const spcies_batch_opts *opts /* or NULL */, spcies_batch_info *info /* or NULL */);  \
+    int NAME##_closed_loop(long B, int steps, const double *x0, const double *xr, const double *ur,       \
+                           double *x_traj, double *u_traj, int *k_traj, int *e_traj,                       \
+                           const spcies_batch_opts *opts /* or NULL */, spcies_batch_info *info /* or NULL */)
 
 /* ellipMPC_ADMM_soc takes the size of the terminal ellipsoid at run time (code_ellipMPC_ADMM_soc_C.c:20) */
 #define SPCIES_CUDA_DECLARE_SOLVER_R(NAME, SOL)                                                            \
@@ -141,7 +155,10 @@ const char *spcies_cuda_last_error(void);
               int *e_flag, SOL *sol);                                                                      \
     int NAME##_batch(long B, const double *x0, const double *xr, const double *ur, const double *r_ellip,  \
                      double *u_opt, int *k, int *e_flag, SOL *sol /* [B] or NULL */,                       \
-                     const spcies_batch_opts *opts /* or NULL */, spcies_batch_info *info /* or NULL */)
+                     const spcies_batch_opts *opts /* or NULL */, spcies_batch_info *info /* or NULL */);  \
+    int NAME##_closed_loop(long B, int steps, const double *x0, const double *xr, const double *ur,       \
+                           const double *r_ellip, double *x_traj, double *u_traj, int *k_traj, int *e_traj, \
+                           const spcies_batch_opts *opts /* or NULL */, spcies_batch_info *info /* or NULL */)
 
 /* ellipHMPC takes three state and three input references, the constant and the two harmonic components of the reference
  * trajectory (header_ellipHMPC_ADMM_C.h:24; code_ellipHMPC_ADMM_C.c:18) */

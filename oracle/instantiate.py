@@ -320,6 +320,31 @@ class RefSolver:
             off += length
         return u, k, e, out
 
+    def closed_loop(self, x0, xr, ur, steps, AB, r=None, threads=1):
+        """Loop of single-instance reference calls with the plant ``x+ = AB (x; u)`` in between (in C, the example's operation
+        order).  Returns ``x [steps+1, B, n], u [steps, B, m], k [steps, B], e [steps, B]``."""
+        x0 = np.ascontiguousarray(np.atleast_2d(x0), dtype=np.float64)
+        xr = np.ascontiguousarray(np.atleast_2d(xr), dtype=np.float64)
+        ur = np.ascontiguousarray(np.atleast_2d(ur), dtype=np.float64)
+        AB = np.ascontiguousarray(AB, dtype=np.float64)
+        B = x0.shape[0]
+        assert AB.shape == (self.n, self.n + self.m)
+        if self.has_r:
+            r = np.ascontiguousarray(np.broadcast_to(np.asarray(r, dtype=np.float64).ravel(), (B,)))
+        xt = np.empty((steps + 1, B, self.n))
+        ut = np.empty((steps, B, self.m))
+        kt = np.empty((steps, B), dtype=np.int32)
+        et = np.empty((steps, B), dtype=np.int32)
+        dp, ip = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int)
+        f = self.lib.spcies_ref_closed_loop
+        f.restype = ctypes.c_int
+        f.argtypes = [ctypes.c_long, ctypes.c_int, dp, dp, dp, dp, dp, dp, dp, ip, ip, ctypes.c_int]
+        rc = f(B, int(steps), self._p(x0), self._p(xr), self._p(ur), self._p(r if self.has_r else None), self._p(AB),
+               self._p(xt), self._p(ut), self._p(kt, ctypes.c_int), self._p(et, ctypes.c_int), int(threads))
+        if rc != 0:
+            raise RuntimeError(f'spcies_ref_closed_loop failed ({rc})')
+        return xt, ut, kt, et
+
     def solve(self, x0, xr, ur, r=None):
         if self.nref == 3:
             xr, ur = [np.asarray(a)[None] for a in xr], [np.asarray(a)[None] for a in ur]

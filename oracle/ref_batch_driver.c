@@ -88,3 +88,72 @@ int spcies_ref_batch(long B, const double *x0, const double *xr, const double *u
     for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
     return 0;
 }
+
+/* Closed loop of reference calls for every instance (examples/cl_in_C/main_cl_in_C.c:100-117): u_t = solver(x_t), then the
+ * successor state accumulated exactly like the example (x_aux[i] += AB[i][j] * x[j]; ... += AB[i][nn_+j] * u[j]).
+ * x_traj [steps + 1][B][nn_], u_traj [steps][B][mm_], k_traj / e_traj [steps][B]; AB row-major [nn_][nn_ + mm_]. */
+#if SPCIES_NREF == 1
+typedef struct {
+    long lo, hi, B;
+    int steps;
+    const double *x0, *xr, *ur, *r, *AB;
+    double *xt, *ut;
+    int *kt, *et;
+} cl_slice_t;
+
+static void *run_cl_slice(void *arg) {
+    cl_slice_t *s = (cl_slice_t *)arg;
+    SPCIES_SOL sol;
+    double x[nn_], xr[nn_], ur[mm_], u[mm_];
+    for (long i = s->lo; i < s->hi; i++) {
+        memcpy(x, s->x0 + i * nn_, sizeof x);
+        memcpy(s->xt + i * nn_, x, sizeof x);
+        for (int t = 0; t < s->steps; t++) {
+            int k = 0, e = 0;
+            double xin[nn_];
+            memcpy(xin, x, sizeof x);
+            memcpy(xr, s->xr + i * nn_, sizeof xr);
+            memcpy(ur, s->ur + i * mm_, sizeof ur);
+            memset(&sol, 0, sizeof sol);
+#if SPCIES_HAS_R
+            double r = s->r[i];
+            SPCIES_FUNC(xin, xr, ur, &r, u, &k, &e, &sol);
+#else
+            SPCIES_FUNC(xin, xr, ur, u, &k, &e, &sol);
+#endif
+            double x_aux[nn_] = {0.0};
+            for (int a = 0; a < nn_; a++) {
+                for (int j = 0; j < nn_; j++) x_aux[a] += s->AB[a * (nn_ + mm_) + j] * x[j];
+                for (int j = 0; j < mm_; j++) x_aux[a] += s->AB[a * (nn_ + mm_) + nn_ + j] * u[j];
+            }
+            memcpy(x, x_aux, sizeof x);
+            memcpy(s->ut + ((long)t * s->B + i) * mm_, u, sizeof u);
+            s->kt[(long)t * s->B + i] = k;
+            s->et[(long)t * s->B + i] = e;
+            memcpy(s->xt + ((long)(t + 1) * s->B + i) * nn_, x, sizeof x);
+        }
+    }
+    return NULL;
+}
+
+int spcies_ref_closed_loop(long B, int steps, const double *x0, const double *xr, const double *ur, const double *r,
+                           const double *AB, double *xt, double *ut, int *kt, int *et, int nthreads) {
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > 256) nthreads = 256;
+    if ((long)nthreads > B) nthreads = B > 0 ? (int)B : 1;
+    pthread_t th[256];
+    cl_slice_t sl[256];
+    long per = (B + nthreads - 1) / nthreads;
+    for (int t = 0; t < nthreads; t++) {
+        long lo = t * per, hi = lo + per;
+        if (lo > B) lo = B;
+        if (hi > B) hi = B;
+        sl[t] = (cl_slice_t){lo, hi, B, steps, x0, xr, ur, r, AB, xt, ut, kt, et};
+    }
+    if (nthreads == 1) { run_cl_slice(&sl[0]); return 0; }
+    for (int t = 0; t < nthreads; t++)
+        if (pthread_create(&th[t], NULL, run_cl_slice, &sl[t]) != 0) return -1;
+    for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
+    return 0;
+}
+#endif

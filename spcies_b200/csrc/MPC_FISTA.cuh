@@ -73,10 +73,6 @@
 #ifndef SPCIES_FISTA_BLOCK2
 #define SPCIES_FISTA_BLOCK2 128      // threads per CTA of the tail launch (one warp per scheduler)
 #endif
-#ifndef SPCIES_FISTA_COOP
-#define SPCIES_FISTA_COOP 0          // 1: the tail launch of FAST-mode calls uses the cooperative kernel (MPC_FISTA_coop.cuh); measured slower
-                                     // than the one-thread-per-instance tail (shared-memory wavefront bound), kept as an experiment
-#endif
 #ifndef SPCIES_FISTA_TAIL_TMEM
 #define SPCIES_FISTA_TAIL_TMEM 0     // 1: the tail launch keeps lambda / w in Tensor Memory as well (fewer shared-memory wavefronts)
 #endif
@@ -710,7 +706,6 @@ __global__ void __launch_bounds__(BLOCK, 1) fista_kernel(const BatchIO io, const
     if constexpr (TM) tmem::free_all(tbase);
 }
 
-#include "MPC_FISTA_coop.cuh"
 #include "MPC_FISTA_mma.cuh"
 
 struct Traits {
@@ -747,11 +742,12 @@ struct Traits {
         return arith != SPCIES_CUDA_ARITH_EXACT && io.sol == nullptr && io.engine != SPCIES_CUDA_ENGINE_SCALAR;
     }
     static bool caps_engine(int arith, const BatchIO &io) { return use_mma(arith, io); }   // iteration-cap rounds
+    static bool cl_engine(int arith, const BatchIO &io) { return use_mma(arith, io) && io.LB == nullptr; }   // closed loop inside the kernel
     static void engine_shape(int arith, const BatchIO &io, int &block, size_t &smem, int &ipb) {
         ipb = block;
         if (use_mma(arith, io)) {
             block = (io.phase != 2 && io.B >= MMA_BULK_MIN) ? MMA_BLOCK_BULK : MMA_BLOCK;
-            smem = block == MMA_BLOCK_BULK ? MMA_BULK_SMEM : MMA_BYTES;
+            smem = MMA_BYTES;
             ipb = block / 4;
         }
     }
@@ -791,14 +787,6 @@ struct Traits {
     }
     static size_t scratch_bytes(int, int, bool) { return 0; }
     static bool uses_scratch(int, const BatchIO &) { return false; }
-    template <bool VARB>
-    static cudaError_t launch_coop(int grid, cudaStream_t s, const BatchIO &io, const void *dc) {
-        auto kern = fista_coop_kernel<VARB>;
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COOP_SMEM);
-        if (e != cudaSuccess) return e;
-        kern<<<grid, COOP_BLOCK, COOP_SMEM, s>>>(io, (const spcies_consts *)dc);
-        return cudaGetLastError();
-    }
     static cudaError_t launch(int arith, bool varb, int grid, int block, size_t smem, cudaStream_t s, const BatchIO &io,
                               const void *dc, void *) {
         const bool ex = arith == SPCIES_CUDA_ARITH_EXACT;
@@ -806,19 +794,19 @@ struct Traits {
         if constexpr (HAS_MMA) {
             if (use_mma(arith, io)) {
                 const bool bulk = block == MMA_BLOCK_BULK && MMA_BLOCK_BULK != MMA_BLOCK;
-                auto kern = bulk ? (varb ? fista_mma_kernel<true, MMA_BLOCK_BULK, BULK_SS> : fista_mma_kernel<false, MMA_BLOCK_BULK, BULK_SS>)
+                auto kern = bulk ? (varb ? fista_mma_kernel<true, MMA_BLOCK_BULK, false> : fista_mma_kernel<false, MMA_BLOCK_BULK, false>)
                                  : (varb ? fista_mma_kernel<true, MMA_BLOCK, false> : fista_mma_kernel<false, MMA_BLOCK, false>);
+                if (io.cl_steps > 0) {      // closed loop: the instances stay on chip across the sampling times (no per-instance bounds)
+                    if (varb) return cudaErrorNotSupported;
+                    kern = bulk ? fista_mma_kernel<false, MMA_BLOCK_BULK, true> : fista_mma_kernel<false, MMA_BLOCK, true>;
+                }
                 if (block != MMA_BLOCK_BULK && block != MMA_BLOCK) return cudaErrorInvalidConfiguration;
-                const size_t sm = bulk ? MMA_BULK_SMEM : MMA_BYTES;
+                const size_t sm = MMA_BYTES;
                 cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
                 if (e != cudaSuccess) return e;
                 kern<<<grid, block, sm, s>>>(io, (const unsigned char *)dc);
                 return cudaGetLastError();
             }
-        }
-        if constexpr (HAS_COOP && SPCIES_FISTA_COOP != 0) {
-            // tail launch, FAST arithmetic, no debug payload: eight lanes per instance
-            if (io.phase == 2 && !ex && io.sol == nullptr) return varb ? launch_coop<true>(grid, s, io, dc) : launch_coop<false>(grid, s, io, dc);
         }
         if (varb) return ex ? launch_b<true, true>(grid, block, smem, s, io, dc) : launch_b<false, true>(grid, block, smem, s, io, dc);
         return ex ? launch_b<true, false>(grid, block, smem, s, io, dc) : launch_b<false, false>(grid, block, smem, s, io, dc);

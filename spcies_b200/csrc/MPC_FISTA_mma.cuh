@@ -50,11 +50,6 @@
 constexpr int MMA_BLOCK = SPCIES_FISTA_MMA_BLOCK;
 constexpr int MMA_BLOCK_BULK = SPCIES_FISTA_MMA_BLOCK_BULK;
 constexpr long long MMA_BULK_MIN = 16LL * 148 * (MMA_BLOCK_BULK / 4);   // batches of at least 16 waves use the bulk configuration
-#ifndef SPCIES_FISTA_MMA_BULK_SMEM
-#define SPCIES_FISTA_MMA_BULK_SMEM 0      // 1: the bulk configuration keeps lambda / mu' in shared memory (MERGE layout only).  Measured
-                                          // slower (tools/variants.py: 10.6 ms at 384 threads, 11.7 ms at 512, against 10.1 ms): the
-                                          // stage-batched products of pass A, not the iterates, hold the registers, so it still spills
-#endif
 constexpr bool MMA_SHAPE_OK = SPCIES_FISTA_MMA != 0 && sizeof(real) == 8 && nm <= 8 && N >= 2 && N <= 12;
 constexpr int MMA_KTAB = k_max + 2;
 constexpr bool PRESCALE = SPCIES_FISTA_MMA_PRESCALE != 0;
@@ -115,8 +110,6 @@ constexpr size_t MMA_OFFSET = BLOB_BYTES;                 // position in the dev
 constexpr size_t TOTAL_BLOB_BYTES = BLOB_BYTES + MMA_BYTES;
 // the tables (the momentum table has k_max + 2 entries) must fit shared memory; otherwise the scalar kernel runs
 constexpr bool HAS_MMA = MMA_SHAPE_OK && MMA_BYTES <= 200 * 1024;
-constexpr bool BULK_SS = SPCIES_FISTA_MMA_BULK_SMEM != 0 && MERGE;
-constexpr size_t MMA_BULK_SMEM = MMA_BYTES + (BULK_SS ? (size_t)2 * N * MMA_BLOCK_BULK * sizeof(double2) : 0);
 
 static inline void fill_mma_tables(const spcies_consts &C, const FistaDerived &D, MmaTables &T) {
     memset(&T, 0, sizeof T);
@@ -222,9 +215,9 @@ __device__ __forceinline__ double2 mma_mat(const double *M, int lane) { return r
 // SS (bulk configuration, MERGE layout only): lambda and mu' live in shared memory as [vector][stage][thread] double2 (one
 // conflict-free 128-bit access per lane) instead of registers; only y stays in registers, so that 4 warps per SM scheduler fit the
 // register file without spills (128 registers) and keep the FP64 pipe busy.
-template <bool VARB, int BLOCK, bool SS>
+// CL: closed-loop run (io.cl_steps sampling times per instance, see the block at the exit test)
+template <bool VARB, int BLOCK, bool CL>
 __global__ void __launch_bounds__(BLOCK, 1) fista_mma_kernel(const BatchIO io, const unsigned char *__restrict__ g_blob) {
-    static_assert(!SS || MERGE, "shared-memory iterates are implemented for the MERGE layout");
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint64_t mbar;
@@ -287,42 +280,26 @@ __global__ void __launch_bounds__(BLOCK, 1) fista_mma_kernel(const BatchIO io, c
     long long inst = -1;
     int k = 0, grace_left = io.grace;
     bool live = false, drained = false, park_ok = io.park != nullptr;
-    double y[N][2], lam[N][2], w[N][2], q[2] = {0, 0}, qT[2] = {0, 0};   // SS: lam / w are not used (the compiler drops them)
-    double2 *sst = reinterpret_cast<double2 *>(smem_raw + MMA_BYTES) + threadIdx.x;   // SS: lambda_l at [l], mu'_l at [N + l]
+    double y[N][2], lam[N][2], w[N][2], q[2] = {0, 0}, qT[2] = {0, 0};
     auto getL = [&](int l, double (&v)[2]) {
-        if constexpr (SS) {
-            const double2 t = sst[l * BLOCK];
-            v[0] = t.x;
-            v[1] = t.y;
-        } else {
-            v[0] = lam[l][0];
-            v[1] = lam[l][1];
-        }
+        v[0] = lam[l][0];
+        v[1] = lam[l][1];
     };
     auto setL = [&](int l, const double (&v)[2]) {
-        if constexpr (SS) sst[l * BLOCK] = make_double2(v[0], v[1]);
-        else {
-            lam[l][0] = v[0];
-            lam[l][1] = v[1];
-        }
+        lam[l][0] = v[0];
+        lam[l][1] = v[1];
     };
     auto getW = [&](int l, double (&v)[2]) {
-        if constexpr (SS) {
-            const double2 t = sst[(N + l) * BLOCK];
-            v[0] = t.x;
-            v[1] = t.y;
-        } else {
-            v[0] = w[l][0];
-            v[1] = w[l][1];
-        }
+        v[0] = w[l][0];
+        v[1] = w[l][1];
     };
     auto setW = [&](int l, const double (&v)[2]) {
-        if constexpr (SS) sst[(N + l) * BLOCK] = make_double2(v[0], v[1]);
-        else {
-            w[l][0] = v[0];
-            w[l][1] = v[1];
-        }
+        w[l][0] = v[0];
+        w[l][1] = v[1];
     };
+    int cl_step = 0;                            // CL: sampling time of the instance this lane group holds
+    bool cl_restart = false;                    // CL: the instance finished a sampling time and starts the next one in place
+    double xnext[2] = {0.0, 0.0};               // CL: its successor state x+ = A x + B u, by column
     double lo0[2] = {0, 0}, hi0[2] = {0, 0};   // "stage -1": lo = hi = x0 on the state components, the bounds of u_0 on the others
 #pragma unroll
     for (int l = 0; l < N; ++l)
@@ -368,10 +345,6 @@ __global__ void __launch_bounds__(BLOCK, 1) fista_mma_kernel(const BatchIO io, c
                             for (int i = 0; i < 2; ++i) {
                                 y[l][i] = xs[i] ? pk[(3 + l * n + xe[i]) * io.park_in_cap] : 0.0;
                                 lam[l][i] = xs[i] ? pk[(3 + N * n + l * n + xe[i]) * io.park_in_cap] : 0.0;
-                            if constexpr (SS) {
-#pragma unroll
-                                for (int l = 0; l < N; ++l) setL(l, lam[l]);
-                            }
                             }
                     } else {
                         k = -1;                                       // the warm-up pass brings it to 0
@@ -379,10 +352,7 @@ __global__ void __launch_bounds__(BLOCK, 1) fista_mma_kernel(const BatchIO io, c
                         for (int l = 0; l < N; ++l)
 #pragma unroll
                             for (int i = 0; i < 2; ++i) y[l][i] = lam[l][i] = 0.0;
-                        if constexpr (SS) {
-#pragma unroll
-                            for (int l = 0; l < N; ++l) setL(l, lam[l]);
-                        }
+                        cl_step = 0;
                     }
                     live = true;
                 }
@@ -401,84 +371,6 @@ __global__ void __launch_bounds__(BLOCK, 1) fista_mma_kernel(const BatchIO io, c
         // (the input part of z_l inside r_l), exact zeros elsewhere; the exit test only looks at state components.
         bool over = false;
         double u0v[2];
-        if constexpr (SS) {
-            // Bulk configuration: the same products, but the stages are taken in groups of G so that the live set of a pass is
-            // G + 1 z vectors, G residuals and G partial products instead of N of each (4 warps per scheduler share the register
-            // file; with that many warps the latency of a group's dependent MMAs is covered by the other warps).
-            constexpr int G = 5;
-            double zprev[2], mu[2] = {0.0, 0.0};
-            {   // "stage -1": (x0, u_0)
-                double a[2];
-                mma_mv(a, nabt, y[0], q[0], q[1]);
-#pragma unroll
-                for (int i = 0; i < 2; ++i) zprev[i] = u0v[i] = clip(a[i], lo0[i], hi0[i]);
-            }
-#pragma unroll
-            for (int g0 = 0; g0 < N; g0 += G) {
-                double zg[G + 1][2], rg[G][2], eg[G][2];
-                zg[0][0] = zprev[0];
-                zg[0][1] = zprev[1];
-#pragma unroll
-                for (int j = 0; j < G; ++j)
-                    if (g0 + j < N - 1) dmma(eg[j][0], eg[j][1], y[g0 + j + 1][0], nabt.x, q[0], q[1]);
-#pragma unroll
-                for (int j = 0; j < G; ++j)
-                    if (g0 + j < N - 1) dmma(zg[j + 1][0], zg[j + 1][1], y[g0 + j + 1][1], nabt.y, eg[j][0], eg[j][1]);
-#pragma unroll
-                for (int j = 0; j < G; ++j) {
-                    const int l = g0 + j;
-                    if (l < N - 1) {
-#pragma unroll
-                        for (int i = 0; i < 2; ++i) {
-                            double lo, hi;
-                            bnd(l + 1, i, lo, hi);
-                            zg[j + 1][i] = clip(fma(qriy[i], y[l][i], zg[j + 1][i]), lo, hi);          // z_l       :494-519
-                        }
-                    } else if (l == N - 1) {
-#if SPCIES_TERMINAL
-#pragma unroll
-                        for (int i = 0; i < 2; ++i) {
-                            double lo, hi;
-                            bnd(N, i, lo, hi);
-                            zg[j + 1][i] = clip(fma(ti[i], y[N - 1][i], qT[i]), lo, hi);              // z_N       :522-537
-                        }
-#else
-                        zg[j + 1][0] = qT[0];
-                        zg[j + 1][1] = qT[1];
-#endif
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < G; ++j)
-                    if (g0 + j < N) dmma(eg[j][0], eg[j][1], zg[j][0], nab.x, zg[j + 1][0], zg[j + 1][1]);
-#pragma unroll
-                for (int j = 0; j < G; ++j)
-                    if (g0 + j < N) dmma(rg[j][0], rg[j][1], zg[j][1], nab.y, eg[j][0], eg[j][1]);          // r_l       :549-572
-#pragma unroll
-                for (int j = 0; j < G; ++j)
-                    if (g0 + j < N) over = over || (fabs(rg[j][0]) > tolv[0]) || (fabs(rg[j][1]) > tolv[1]);
-#pragma unroll
-                for (int j = 0; j < G; ++j)
-                    if (g0 + j < N) dmma(eg[j][0], eg[j][1], rg[j][0], T->FWa[g0 + j][lane].x, 0.0, 0.0);
-#pragma unroll
-                for (int j = 0; j < G; ++j) {
-                    const int l = g0 + j;
-                    if (l < N) {
-                        if (l == 0) {
-                            dmma(mu[0], mu[1], rg[j][1], T->FWb[0][lane], eg[j][0], eg[j][1]);
-                        } else {
-                            double f0, f1;
-                            dmma(f0, f1, mu[0], T->FWa[l][lane].y, eg[j][0], eg[j][1]);
-                            dmma(mu[0], mu[1], lo2 ? rg[j][1] : mu[1], T->FWb[l][lane], f0, f1);
-                        }
-                        setW(l, mu);
-                    }
-                }
-                constexpr int LAST = G;
-                zprev[0] = zg[LAST][0];
-                zprev[1] = zg[LAST][1];
-            }
-        } else {
         double zz[N + 1][2];   // zz[0] = (x0, u_0), zz[l+1] = z_l (l < N-1), zz[N] = z_N (lax) | xr (equ)
         {
             // QRi o (q - [A B]' y_s) for every stage s                                      :474-519
@@ -566,8 +458,6 @@ __global__ void __launch_bounds__(BLOCK, 1) fista_mma_kernel(const BatchIO io, c
             }
             mma_mv(w[N - 1], mma_mat(T->Uinv[N - 1], lane), mu, 0.0, 0.0);
         }
-
-        }
         // ================= exit condition                                            :337-361 =================
         if (live) k += 1;
         const bool gover = (__ballot_sync(FULL, over) & gmask) != 0u;
@@ -576,29 +466,58 @@ __global__ void __launch_bounds__(BLOCK, 1) fista_mma_kernel(const BatchIO io, c
             if (!gover) ef = 1;
             else if (k >= k_max) ef = -1;
             if (ef != 0) {
+                const long long o = CL ? (long long)cl_step * io.cl_ld + inst : inst;   // CL: trajectories are [step][instance]
 #pragma unroll
                 for (int i = 0; i < 2; ++i)
-                    if (us[i]) io.u[inst * m + ue[i]] = eng_u_out(C, u0v[i], ue[i]);
+                    if (us[i]) io.u[o * m + ue[i]] = eng_u_out(C, u0v[i], ue[i]);
                 if (leader) {
-                    io.k[inst] = k;
-                    io.e[inst] = ef;
+                    io.k[o] = k;
+                    io.e[o] = ef;
                     stat_k += (unsigned long long)k;
                     stat_nc += (ef < 0);
                 }
                 live = false;
+                if (CL) cl_restart = cl_step + 1 < io.cl_steps;
+            }
+        }
+        if constexpr (CL) {
+            // Closed loop (examples/cl_in_C/main_cl_in_C.c:100-117 for every instance of the batch, without leaving the chip): the
+            // plant is the prediction model, and -[A B] (x, u_0) is the product the residual r_0 already uses, so the successor
+            // state comes out of one more MMA in the column layout of x -- no shuffles.  The instance then restarts in place:
+            // x0 <- x+, k <- -1 (warm-up pass), and either y = lambda = 0 (cold start, what a loop of reference calls does) or the
+            // y of the exit test kept as the starting dual point (io.cl_warm: the `lambda` argument of
+            // platforms/Matlab/spcies_laxMPC_FISTA_solver.m:161-164, :266-283 -- sol.lambda of the previous sampling time).
+            if (__any_sync(FULL, cl_restart)) {
+                double nx[2];
+                mma_mv(nx, nab, zz[0], 0.0, 0.0);                  // -(A x + B u_0)
+                if (cl_restart) {
+                    cl_step += 1;
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        xnext[i] = -nx[i];
+                        if (xs[i]) {
+                            lo0[i] = hi0[i] = xnext[i];
+                            if (io.cl_x) io.cl_x[((long long)cl_step * io.cl_ld + inst) * n + xe[i]] = xnext[i];
+                        }
+                    }
+                    k = -1;
+                    live = true;
+                }
             }
         }
 
         // ================= pass B: backward step, lambda and y updates      :368-385, :619-648 =================
         const double beta = T->beta[(live && k > 0) ? k : 0];
+        const bool hold = CL && cl_restart;                         // this pass belongs to no iteration of a restarting instance
+        const double hkeep = (CL && io.cl_warm != 0) ? 1.0 : 0.0;
         auto update = [&](int l, const double (&d)[2]) {
-#pragma unroll
             double l1[2], ln[2];
             getL(l, l1);
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
                 ln[i] = y[l][i] + d[i];                             // lambda_l = y_l + d_lambda_l
-                y[l][i] = fma(beta, ln[i] - l1[i], ln[i]);          // y_l = lambda_l + beta (lambda_l - lambda1_l)
+                const double yn = fma(beta, ln[i] - l1[i], ln[i]);  // y_l = lambda_l + beta (lambda_l - lambda1_l)
+                y[l][i] = hold ? hkeep * y[l][i] : yn;
             }
             setL(l, ln);
         };
@@ -630,6 +549,18 @@ __global__ void __launch_bounds__(BLOCK, 1) fista_mma_kernel(const BatchIO io, c
                 if (l < N - 1) mma_mv(d, mma_mat(T->NG[l], lane), d, w[l][0], w[l][1]);   // d_lambda_l = w_l - G_l d_lambda_{l+1}
                 update(l, d);
             }
+        }
+
+        if constexpr (CL) {
+            // io.cl_warm == 2: the receding horizon moved by one stage, so does the dual starting point (lambda_l <- lambda_{l+1},
+            // the last block is repeated)
+            if (io.cl_warm == 2 && __any_sync(FULL, cl_restart)) {
+#pragma unroll
+                for (int l = 0; l < N - 1; ++l)
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) y[l][i] = cl_restart ? y[l + 1][i] : y[l][i];
+            }
+            cl_restart = false;
         }
 
         // ---- parking: an instance that is still running `grace` iterations after the queue ran dry (io.phase 1), or that

@@ -177,7 +177,12 @@ struct BatchIO {
     int cap;                          // > 0: park an instance once it has done `cap` iterations (MPC_FISTA_mma.cuh)
     int engine;                       // spcies_batch_opts.engine (kernels with more than one engine, MPC_FISTA.cuh)
     const unsigned long long *ready;  // optional: instances [0, *ready) have their inputs in device memory (the host->device
-                                      // copies of a host-buffer call run on a second stream, chunk by chunk, under the kernel)
+                                      // copies of a host-buffer call run on a second stream, chunk by chunk, under the kernel)    // closed-loop runs of engines that keep an instance on chip across sampling times (Traits::cl_engine, MPC_FISTA_mma.cuh):
+    // u / k / e are trajectories [cl_steps][cl_ld][..], x0 is sampling time 0, cl_x (optional) receives x at times 1..cl_steps
+    int cl_steps;                     // 0: an ordinary batched call
+    int cl_warm;                      // 1: the dual point of the previous sampling time is the starting point of the next
+    long long cl_ld;                  // instances per sampling time in the trajectory arrays
+    double *cl_x;                     // [cl_steps + 1][cl_ld][nn_] or nullptr
 };
 constexpr int QUEUE_WORDS = 16;   // [8]: number of instances whose inputs have arrived (pipelined host->device copies)
 

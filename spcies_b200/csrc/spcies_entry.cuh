@@ -109,6 +109,11 @@ int SPCIES_CAT(SPCIES_FUNC, _batch)(long B, const double *x0, const double *xr, 
                                     const spcies_batch_opts *opts, spcies_batch_info *info) {
     return ::spcies::RT::get().run(B, x0, xr, ur, r_ellip, u_opt, k, e_flag, reinterpret_cast<double *>(sol), opts, info);
 }
+int SPCIES_CAT(SPCIES_FUNC, _closed_loop)(long B, int steps, const double *x0, const double *xr, const double *ur, const double *r_ellip,
+                                          double *x_traj, double *u_traj, int *k_traj, int *e_traj, const spcies_batch_opts *opts,
+                                          spcies_batch_info *info) {
+    return ::spcies::RT::get().run_closed_loop(B, steps, x0, xr, ur, r_ellip, x_traj, u_traj, k_traj, e_traj, opts, info, spcies_model_AB);
+}
 #else
 void SPCIES_FUNC(double *x0_in, double *xr_in, double *ur_in, double *u_opt, int *k_in, int *e_flag, SPCIES_SOL_T *sol) {
     ::spcies::single_instance(x0_in, xr_in, ur_in, nullptr, u_opt, k_in, e_flag, sol);
@@ -117,6 +122,11 @@ int SPCIES_CAT(SPCIES_FUNC, _batch)(long B, const double *x0, const double *xr, 
                                     int *e_flag, SPCIES_SOL_T *sol, const spcies_batch_opts *opts,
                                     spcies_batch_info *info) {
     return ::spcies::RT::get().run(B, x0, xr, ur, nullptr, u_opt, k, e_flag, reinterpret_cast<double *>(sol), opts, info);
+}
+int SPCIES_CAT(SPCIES_FUNC, _closed_loop)(long B, int steps, const double *x0, const double *xr, const double *ur, double *x_traj,
+                                          double *u_traj, int *k_traj, int *e_traj, const spcies_batch_opts *opts,
+                                          spcies_batch_info *info) {
+    return ::spcies::RT::get().run_closed_loop(B, steps, x0, xr, ur, nullptr, x_traj, u_traj, k_traj, e_traj, opts, info, spcies_model_AB);
 }
 #endif
 

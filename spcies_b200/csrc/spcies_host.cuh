@@ -70,7 +70,35 @@ struct DeviceCtx {
     double *d_park = nullptr;    // parked-instance records (tail handling, Traits::HAS_PARK)
     double *d_park2 = nullptr;   // second record buffer of the iteration-cap rounds (a round resumes from one, parks into the other)
     long long cap_park = 0;
+    // closed-loop trajectories (run_closed_loop): x [steps + 1][B][nn_], u [steps][B][mm_], k / e [steps][B]; the plant [A B]
+    double *d_clx = nullptr, *d_clu = nullptr, *d_plant = nullptr;
+    int *d_clk = nullptr, *d_cle = nullptr;
+    long long cap_cl = 0;        // capacity in (steps + 1) * B units
 };
+
+// x+ = [A B] (x; u) for every instance, accumulated in the order of examples/cl_in_C/main_cl_in_C.c:104-113 with individually
+// rounded operations (what gcc -O3 emits for x86-64): the trajectories of a closed-loop run in EXACT arithmetic are bit-identical
+// to a loop of reference calls.
+template <int NN, int MM>
+__global__ void cl_plant_kernel(long long B, const double *__restrict__ AB, const double *__restrict__ x, const double *__restrict__ u,
+                                double *__restrict__ xn) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    double xv[NN], uv[MM];
+#pragma unroll
+    for (int j = 0; j < NN; ++j) xv[j] = x[i * NN + j];
+#pragma unroll
+    for (int j = 0; j < MM; ++j) uv[j] = u[i * MM + j];
+#pragma unroll
+    for (int r = 0; r < NN; ++r) {
+        double a = 0.0;
+#pragma unroll
+        for (int j = 0; j < NN; ++j) a = __dadd_rn(a, __dmul_rn(AB[r * (NN + MM) + j], xv[j]));
+#pragma unroll
+        for (int j = 0; j < MM; ++j) a = __dadd_rn(a, __dmul_rn(AB[r * (NN + MM) + NN + j], uv[j]));
+        xn[i * NN + r] = a;
+    }
+}
 
 template <class Traits> struct Runtime {
     std::vector<DeviceCtx> ctx;
@@ -125,11 +153,14 @@ template <class Traits> struct Runtime {
         SPCIES_CK(cudaMalloc((void **)p, (size_t)count * sizeof(P)));
         return 0;
     }
+    // a failed allocation leaves *p == nullptr: the capacities are cleared first so that no later, smaller call trusts them
+    static void drop_caps(DeviceCtx &c) { c.cap = c.cap_b = c.cap_sol = c.cap_cl = 0; }
 
     int reserve(DeviceCtx &c, long long B, bool varb, bool sol) {
         if (B > c.cap) {
             long long n = B + B / 8 + 64;
             int rc;
+            c.cap = 0;
             if ((rc = grow(&c.d_x0, n * Traits::NN))) return rc;
             if ((rc = grow(&c.d_xr, n * Traits::NN))) return rc;
             if ((rc = grow(&c.d_ur, n * Traits::MM))) return rc;
@@ -147,12 +178,14 @@ template <class Traits> struct Runtime {
         }
         if (varb && B > c.cap_b) {
             int rc;
+            c.cap_b = 0;
             if ((rc = grow(&c.d_LB, B * Traits::NMM))) return rc;
             if ((rc = grow(&c.d_UB, B * Traits::NMM))) return rc;
             c.cap_b = B;
         }
         if (sol && B > c.cap_sol) {
             int rc;
+            c.cap_sol = 0;
             if ((rc = grow(&c.d_sol, B * (long long)Traits::SOL_DOUBLES))) return rc;
             c.cap_sol = B;
         }
@@ -166,6 +199,7 @@ template <class Traits> struct Runtime {
             cudaFree(c.d_consts); cudaFree(c.d_queue);
             cudaFree(c.d_x0); cudaFree(c.d_xr); cudaFree(c.d_ur); cudaFree(c.d_r); cudaFree(c.d_LB); cudaFree(c.d_UB);
             cudaFree(c.d_xr2); cudaFree(c.d_xr3); cudaFree(c.d_ur2); cudaFree(c.d_ur3);
+            cudaFree(c.d_clx); cudaFree(c.d_clu); cudaFree(c.d_clk); cudaFree(c.d_cle); cudaFree(c.d_plant);
             cudaFree(c.d_u); cudaFree(c.d_sol); cudaFree(c.d_k); cudaFree(c.d_e); cudaFree(c.d_scratch); cudaFree(c.d_park); cudaFree(c.d_park2);
             for (auto &e : c.ev) cudaEventDestroy(e);
             cudaStreamDestroy(c.stream);
@@ -261,6 +295,7 @@ template <class Traits> struct Runtime {
         if (grid > c.sm_count) grid = c.sm_count;
         const size_t need_scratch = Traits::uses_scratch(cl.arith, io) ? Traits::scratch_bytes(grid, block, varb) : 0;
         if (need_scratch > c.cap_scratch) {
+            c.cap_scratch = 0;
             if (c.d_scratch) SPCIES_CK(cudaFree(c.d_scratch));
             c.d_scratch = nullptr;
             SPCIES_CK(cudaMalloc(&c.d_scratch, need_scratch));
@@ -340,6 +375,7 @@ template <class Traits> struct Runtime {
         if (want < grid) grid = (int)(want > 0 ? want : 1);
         const size_t need_scratch = Traits::uses_scratch(cl.arith, io) ? Traits::scratch_bytes(grid, block, varb) : 0;
         if (need_scratch > c.cap_scratch) {
+            c.cap_scratch = 0;
             if (c.d_scratch) SPCIES_CK(cudaFree(c.d_scratch));
             c.d_scratch = nullptr;
             SPCIES_CK(cudaMalloc(&c.d_scratch, need_scratch));
@@ -487,6 +523,196 @@ template <class Traits> struct Runtime {
             res.drain_us = (int)((t_drain - t_start) / 1000ULL);
         }
         res.block = block; res.grid = grid; res.smem = (int)smem;
+        return 0;
+    }
+
+    // ---- closed loop -------------------------------------------------------------------------------------------------------------
+    struct ClCall {
+        long long B, ld;                       // instances of this device's slice; instances per sampling time in the caller's arrays
+        int steps;
+        const double *x0, *xr, *ur, *r, *plant;
+        double *x_traj, *u_traj;
+        int *k_traj, *e_traj;
+        int arith, engine, warm;
+        bool model_plant;
+    };
+    int cl_on_device(int dev, const ClCall &cl, Result &res) {
+        DeviceCtx *pc;
+        int rc = init_device(dev, &pc);
+        if (rc) return rc;
+        DeviceCtx &c = *pc;
+        const long long B = cl.B;
+        const int steps = cl.steps;
+        if ((rc = reserve(c, B, false, false))) return rc;
+        const long long need = (long long)(steps + 1) * B;
+        if (need > c.cap_cl) {
+            c.cap_cl = 0;
+            if ((rc = grow(&c.d_clx, need * Traits::NN))) return rc;
+            if ((rc = grow(&c.d_clu, need * Traits::MM))) return rc;
+            if ((rc = grow(&c.d_clk, need))) return rc;
+            if ((rc = grow(&c.d_cle, need))) return rc;
+            c.cap_cl = need;
+        }
+        if (!c.d_plant) SPCIES_CK(cudaMalloc((void **)&c.d_plant, sizeof(double) * Traits::NN * Traits::NMM));
+        cudaStream_t s = c.stream;
+        SPCIES_CK(cudaEventRecord(c.ev[0], s));
+        SPCIES_CK(cudaMemcpyAsync(c.d_plant, cl.plant, sizeof(double) * Traits::NN * Traits::NMM, cudaMemcpyHostToDevice, s));
+        SPCIES_CK(cudaMemcpyAsync(c.d_clx, cl.x0, (size_t)B * Traits::NN * 8, cudaMemcpyHostToDevice, s));
+        SPCIES_CK(cudaMemcpyAsync(c.d_xr, cl.xr, (size_t)B * Traits::NN * 8, cudaMemcpyHostToDevice, s));
+        SPCIES_CK(cudaMemcpyAsync(c.d_ur, cl.ur, (size_t)B * Traits::MM * 8, cudaMemcpyHostToDevice, s));
+        if (Traits::HAS_R) SPCIES_CK(cudaMemcpyAsync(c.d_r, cl.r, (size_t)B * 8, cudaMemcpyHostToDevice, s));
+        BatchIO io;
+        memset(&io, 0, sizeof io);
+        io.B = B;
+        io.queue = c.d_queue;
+        io.xr = c.d_xr; io.ur = c.d_ur; io.r = c.d_r;
+        io.engine = cl.engine;
+        io.grace = 1 << 30;
+        int block = Traits::default_block(false), ipb = block;
+        size_t smem = Traits::smem_bytes(block, false);
+        Traits::engine_shape(cl.arith, io, block, smem, ipb);
+        long long want = (B + ipb - 1) / ipb;
+        int grid = c.sm_count;
+        if (want < grid) grid = (int)(want > 0 ? want : 1);
+        const size_t need_scratch = Traits::uses_scratch(cl.arith, io) ? Traits::scratch_bytes(grid, block, false) : 0;
+        if (need_scratch > c.cap_scratch) {
+            c.cap_scratch = 0;
+            if (c.d_scratch) SPCIES_CK(cudaFree(c.d_scratch));
+            c.d_scratch = nullptr;
+            SPCIES_CK(cudaMalloc(&c.d_scratch, need_scratch));
+            c.cap_scratch = need_scratch;
+        }
+        std::vector<unsigned long long> stats((size_t)QUEUE_WORDS * (steps > 0 ? steps : 1), 0ULL);
+        SPCIES_CK(cudaEventRecord(c.ev[1], s));
+        const bool in_kernel = cl.model_plant && Traits::cl_engine(cl.arith, io) && B > 0 && steps > 0;
+        if (in_kernel) {
+            // the engine keeps every instance on chip for the whole run: one launch
+            io.x0 = c.d_clx; io.u = c.d_clu; io.k = c.d_clk; io.e = c.d_cle;
+            io.cl_steps = steps; io.cl_warm = cl.warm; io.cl_ld = B; io.cl_x = c.d_clx;
+            SPCIES_CK(cudaMemsetAsync(c.d_queue, 0, QUEUE_WORDS * sizeof(unsigned long long), s));
+            SPCIES_CK(Traits::launch(cl.arith, false, grid, block, smem, s, io, c.d_consts, c.d_scratch));
+            SPCIES_CK(cudaMemcpyAsync(stats.data(), c.d_queue, QUEUE_WORDS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+            res.launches = 1;
+        } else if (B > 0) {
+            for (int t = 0; t < steps; ++t) {
+                io.x0 = c.d_clx + (size_t)t * B * Traits::NN;
+                io.u = c.d_clu + (size_t)t * B * Traits::MM;
+                io.k = c.d_clk + (size_t)t * B;
+                io.e = c.d_cle + (size_t)t * B;
+                SPCIES_CK(cudaMemsetAsync(c.d_queue, 0, QUEUE_WORDS * sizeof(unsigned long long), s));
+                SPCIES_CK(Traits::launch(cl.arith, false, grid, block, smem, s, io, c.d_consts, c.d_scratch));
+                SPCIES_CK(cudaMemcpyAsync(stats.data() + (size_t)t * QUEUE_WORDS, c.d_queue, QUEUE_WORDS * sizeof(unsigned long long),
+                                          cudaMemcpyDeviceToHost, s));
+                cl_plant_kernel<Traits::NN, Traits::MM><<<(unsigned)((B + 127) / 128), 128, 0, s>>>(
+                    B, c.d_plant, io.x0, io.u, c.d_clx + (size_t)(t + 1) * B * Traits::NN);
+                SPCIES_CK(cudaGetLastError());
+                res.launches += 2;
+            }
+        }
+        SPCIES_CK(cudaEventRecord(c.ev[2], s));
+        if (B > 0 && steps > 0) {
+            const size_t w8 = (size_t)B * 8, w4 = (size_t)B * 4;
+            if (cl.x_traj)
+                SPCIES_CK(cudaMemcpy2DAsync(cl.x_traj, (size_t)cl.ld * Traits::NN * 8, c.d_clx, w8 * Traits::NN, w8 * Traits::NN, steps + 1,
+                                            cudaMemcpyDeviceToHost, s));
+            SPCIES_CK(cudaMemcpy2DAsync(cl.u_traj, (size_t)cl.ld * Traits::MM * 8, c.d_clu, w8 * Traits::MM, w8 * Traits::MM, steps,
+                                        cudaMemcpyDeviceToHost, s));
+            SPCIES_CK(cudaMemcpy2DAsync(cl.k_traj, (size_t)cl.ld * 4, c.d_clk, w4, w4, steps, cudaMemcpyDeviceToHost, s));
+            SPCIES_CK(cudaMemcpy2DAsync(cl.e_traj, (size_t)cl.ld * 4, c.d_cle, w4, w4, steps, cudaMemcpyDeviceToHost, s));
+        }
+        SPCIES_CK(cudaEventRecord(c.ev[3], s));
+        SPCIES_CK(cudaStreamSynchronize(s));
+        SPCIES_CK(cudaGetLastError());
+        float ms = 0;
+        SPCIES_CK(cudaEventElapsedTime(&ms, c.ev[1], c.ev[2]));
+        res.kernel_ms = ms;
+        SPCIES_CK(cudaEventElapsedTime(&ms, c.ev[0], c.ev[1]));
+        res.h2d_ms = ms;
+        SPCIES_CK(cudaEventElapsedTime(&ms, c.ev[2], c.ev[3]));
+        res.d2h_ms = ms;
+        for (int t = 0; t < (in_kernel ? 1 : steps); ++t) {
+            res.sum_k += (long long)stats[(size_t)t * QUEUE_WORDS + 1];
+            res.n_nc += (long long)stats[(size_t)t * QUEUE_WORDS + 2];
+        }
+        res.block = block; res.grid = grid; res.smem = (int)smem;
+        return 0;
+    }
+
+    int run_closed_loop(long long B, int steps, const double *x0, const double *xr, const double *ur, const double *r, double *x_traj,
+                        double *u_traj, int *k_traj, int *e_traj, const spcies_batch_opts *opts, spcies_batch_info *info,
+                        const double *model_AB) {
+        auto t0 = std::chrono::steady_clock::now();
+        spcies_batch_opts o;
+        memset(&o, 0, sizeof o);
+        if (opts) o = *opts;
+        if (B < 0 || steps < 0) return fail(SPCIES_CUDA_EINVAL, "B < 0 or steps < 0");
+        if (o.warm_start < 0 || o.warm_start > 2) return fail(SPCIES_CUDA_EINVAL, "warm_start must be 0, 1 or 2");
+        if (Traits::NREF != 1) return fail(SPCIES_CUDA_EUNSUPPORTED, "closed loop: not available for solvers with three references");
+        if (B > 0 && steps > 0 && (!x0 || !xr || !ur || !u_traj || !k_traj || !e_traj || (Traits::HAS_R && !r)))
+            return fail(SPCIES_CUDA_EINVAL, "NULL array argument");
+        if (o.device_pointers || o.LB || o.UB) return fail(SPCIES_CUDA_EUNSUPPORTED, "closed loop: host arrays, generated bounds");
+        if (o.arith != SPCIES_CUDA_ARITH_FAST && o.arith != SPCIES_CUDA_ARITH_EXACT) return fail(SPCIES_CUDA_EINVAL, "unknown arith mode");
+        int ndev = o.n_devices > 1 ? o.n_devices : 1;
+        int avail = device_count();
+        if (avail <= 0) return fail(SPCIES_CUDA_ENODEVICE, "no usable CUDA device (this library has no CPU fallback)");
+        if (o.device < 0 || o.device + ndev > avail) return fail(SPCIES_CUDA_ENODEVICE, "requested CUDA devices do not exist");
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            if ((int)ctx.size() < avail) ctx.resize(avail);
+        }
+        std::vector<Result> res(ndev);
+        std::vector<ClCall> calls(ndev);
+        const long long per = (B + ndev - 1) / ndev;
+        for (int d = 0; d < ndev; ++d) {
+            long long lo = std::min<long long>(B, d * per), hi = std::min<long long>(B, lo + per);
+            ClCall &c = calls[d];
+            c.B = hi - lo; c.ld = B; c.steps = steps;
+            c.x0 = x0 + lo * Traits::NN; c.xr = xr + lo * Traits::NN; c.ur = ur + lo * Traits::MM; c.r = r ? r + lo : nullptr;
+            c.plant = o.plant_AB ? o.plant_AB : model_AB;
+            c.model_plant = o.plant_AB == nullptr;
+            c.x_traj = x_traj ? x_traj + lo * Traits::NN : nullptr;
+            c.u_traj = u_traj + lo * Traits::MM; c.k_traj = k_traj + lo; c.e_traj = e_traj + lo;
+            c.arith = o.arith; c.engine = o.engine; c.warm = o.warm_start;
+        }
+        if (o.warm_start) {
+            BatchIO probe;
+            memset(&probe, 0, sizeof probe);
+            probe.engine = o.engine;
+            if (!Traits::cl_engine(o.arith, probe) || o.plant_AB)
+                return fail(SPCIES_CUDA_EUNSUPPORTED, "warm start needs the FISTA tensor-core engine (FAST arithmetic, model plant)");
+        }
+        if (ndev == 1) {
+            res[0].rc = cl_on_device(o.device, calls[0], res[0]);
+        } else {
+            std::vector<std::thread> th;
+            std::vector<std::string> errs(ndev);
+            for (int d = 0; d < ndev; ++d)
+                th.emplace_back([&, d] {
+                    res[d].rc = cl_on_device(o.device + d, calls[d], res[d]);
+                    if (res[d].rc) errs[d] = g_last_error;
+                });
+            for (auto &t : th) t.join();
+            for (int d = 0; d < ndev; ++d)
+                if (res[d].rc) snprintf(g_last_error, sizeof g_last_error, "device %d: %s", o.device + d, errs[d].c_str());
+        }
+        for (int d = 0; d < ndev; ++d)
+            if (res[d].rc) return res[d].rc;
+        if (info) {
+            memset(info, 0, sizeof *info);
+            for (int d = 0; d < ndev; ++d) {
+                info->kernel_ms = std::max(info->kernel_ms, res[d].kernel_ms);
+                info->h2d_ms = std::max(info->h2d_ms, res[d].h2d_ms);
+                info->d2h_ms = std::max(info->d2h_ms, res[d].d2h_ms);
+                info->sum_k += res[d].sum_k;
+                info->n_not_converged += res[d].n_nc;
+                info->launches += res[d].launches;
+            }
+            info->block_threads = res[0].block; info->grid_blocks = res[0].grid; info->smem_bytes = res[0].smem;
+            info->n_devices = ndev;
+            info->h2d_bytes = B * 8 * (2 * Traits::NN + Traits::MM + (Traits::HAS_R ? 1 : 0));
+            info->d2h_bytes = B * (long long)steps * (8 * Traits::MM + 8) + (x_traj ? B * (long long)(steps + 1) * 8 * Traits::NN : 0);
+            info->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        }
         return 0;
     }
 

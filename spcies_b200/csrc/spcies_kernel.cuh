@@ -131,6 +131,7 @@ template <class S> struct PolicyTraits {
     static int resume_block(bool varb) { return default_block(varb); }
     static void engine_shape(int, const BatchIO &, int &block, size_t &, int &ipb) { ipb = block; }
     static bool caps_engine(int, const BatchIO &) { return false; }
+    static bool cl_engine(int, const BatchIO &) { return false; }     // no in-kernel closed loop: one launch per sampling time
     static bool uses_scratch(int, const BatchIO &) { return true; }   // the global per-instance state of the scalar kernels
     static constexpr int K_MAX = 0;
     static cudaError_t init_device_symbols() { return cudaSuccess; }

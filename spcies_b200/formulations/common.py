@@ -42,6 +42,7 @@ class SolverSpec:
     sol_fields: tuple = ()         # (name, length) of the sol_<name> debug payload
     vars: dict = field(default_factory=dict)
     dims: dict = field(default_factory=dict)
+    model: tuple = ()              # (A, B) of the prediction model (the default plant of the closed-loop entry point)
 
     def define(self, name, default=None):
         for r in self.defines:

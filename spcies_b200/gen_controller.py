@@ -37,6 +37,9 @@ def make_spec(sys=None, param=None, **kw):
         raise NotImplementedError(f'cons_{key}_{opt.platform}: this formulation/method is not available')
     spec = CONSTRUCTORS[key](recipe)
     spec.options = opt
+    from .formulations.common import get_sys_param
+    A, B = get_sys_param(recipe)[:2]
+    spec.model = (A, B)
     return spec
 
 

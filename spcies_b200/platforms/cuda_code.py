@@ -140,7 +140,10 @@ def emit_text(spec, save_name):
     cu += [_member_decl(r) for r in rows]
     cu += ['};', '', 'static const spcies_consts spcies_h_consts = {']
     cu.append(',\n'.join(_member_init(r) for r in rows))
-    cu += ['};', '', f'#include "{kernel_hdr}"', '',
+    # the prediction model [A B], row-major: the default plant of <func>_closed_loop (exact round trip: 17 significant digits)
+    AB = np.hstack([np.asarray(spec.model[0], float), np.asarray(spec.model[1], float)])
+    cu += ['};', '', 'static const double spcies_model_AB[nn_ * nm_] = {' + ', '.join('%.17g' % v for v in AB.ravel()) + '};']
+    cu += ['', f'#include "{kernel_hdr}"', '',
            '// This code is generated by the CUDA platform of spcies_b200 for the Spcies toolbox: '
            'https://github.com/GepocUS/Spcies', '']
     return '\n'.join(h), '\n'.join(cu)

@@ -21,7 +21,7 @@ class BatchOpts(ctypes.Structure):
     _fields_ = [('device', c_int), ('n_devices', c_int), ('arith', c_int), ('device_pointers', c_int),
                 ('LB', c_void_p), ('UB', c_void_p), ('stream', c_void_p),
                 ('block_threads', c_int), ('grid_blocks', c_int), ('tail_mode', c_int), ('tail_grace', c_int),
-                ('engine', c_int), ('tail_caps', c_int * 3), ('reserved', c_int * 2)]
+                ('engine', c_int), ('tail_caps', c_int * 3), ('warm_start', c_int), ('reserved', c_int * 1), ('plant_AB', c_void_p)]
 
 
 class BatchInfo(ctypes.Structure):
@@ -74,6 +74,9 @@ class CudaSolver:
         self._single.restype = None
         self._batch = getattr(L, self.func_name + '_batch')
         self._batch.restype = c_int
+        self._closed_loop = getattr(L, self.func_name + '_closed_loop', None)
+        if self._closed_loop is not None:
+            self._closed_loop.restype = c_int
         self.sol_fields = tuple(spec.sol_fields) if spec is not None else ()
 
     def _guess_func(self):
@@ -184,6 +187,48 @@ class CudaSolver:
         if want_sol:
             return u, k, e, info.as_dict(), self._split_sol(sol)
         return u, k, e, info.as_dict()
+
+    def closed_loop(self, x0, xr, ur, steps, r=None, warm_start=False, plant_AB=None, arith=ARITH_FAST, device=0, n_devices=1,
+                    engine=0, want_x=True):
+        """``steps`` sampling times of the closed loop ``u_t = MPC(x_t)``, ``x_{t+1} = A x_t + B u_t`` for every instance (the loop
+        of examples/cl_in_C/main_cl_in_C.c:100-117, batched and device-resident) through ``<func>_closed_loop``.
+        Returns ``x [steps+1, B, n] (or None), u [steps, B, m], k [steps, B], e_flag [steps, B], info``."""
+        if self._closed_loop is None:
+            raise SpciesCudaError('this solver has no closed-loop entry point')
+        x0 = np.ascontiguousarray(x0, dtype=np.float64)
+        xr = np.ascontiguousarray(xr, dtype=np.float64)
+        ur = np.ascontiguousarray(ur, dtype=np.float64)
+        B = x0.shape[0] if x0.ndim == 2 else 0
+        if x0.shape != (B, self.n) or xr.shape != (B, self.n) or ur.shape != (B, self.m):
+            raise ValueError('x0 / xr / ur must be [B, nn_], [B, nn_], [B, mm_]')
+        steps = int(steps)
+        x = np.empty((steps + 1, B, self.n)) if want_x else None
+        u = np.empty((steps, B, self.m))
+        k = np.empty((steps, B), dtype=np.int32)
+        e = np.empty((steps, B), dtype=np.int32)
+        opts = BatchOpts()
+        opts.device, opts.n_devices, opts.arith, opts.engine = int(device), int(n_devices), int(arith), int(engine)
+        opts.warm_start = int(warm_start)            # 0 cold, 1 previous dual point, 2 previous dual point shifted by one stage
+        keep = []
+        if plant_AB is not None:
+            pab = np.ascontiguousarray(plant_AB, dtype=np.float64)
+            if pab.shape != (self.n, self.n + self.m):
+                raise ValueError('plant_AB must be [nn_, nm_]')
+            opts.plant_AB = pab.ctypes.data
+            keep.append(pab)
+        info = BatchInfo()
+        args = [c_long(B), c_int(steps), _dptr(x0), _dptr(xr), _dptr(ur)]
+        if self.has_r:
+            if r is None:
+                raise ValueError('this solver takes the size of the terminal ellipsoid: r [B] is required')
+            rr = np.ascontiguousarray(np.broadcast_to(np.asarray(r, dtype=np.float64).ravel(), (B,)))
+            keep.append(rr)
+            args.append(_dptr(rr))
+        args += [_dptr(x), _dptr(u), _dptr(k), _dptr(e), ctypes.byref(opts), ctypes.byref(info)]
+        rc = self._closed_loop(*args)
+        if rc != 0:
+            raise SpciesCudaError(f'{self.func_name}_closed_loop failed ({rc}): {self.last_error()}')
+        return x, u, k, e, info.as_dict()
 
     def solve_batch_device(self, B, d_x0, d_xr, d_ur, d_u, d_k, d_e, d_r=None, d_LB=None, d_UB=None, arith=ARITH_FAST,
                            device=0, stream=None, block_threads=0, grid_blocks=0, tail_mode=0, tail_grace=0, engine=0, tail_caps=()):

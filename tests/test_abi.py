@@ -39,7 +39,9 @@ def test_library_exports_declared_symbols(name):
     lib.spcies_cuda_save_name.restype = ctypes.c_char_p
     assert lib.spcies_cuda_save_name().decode() == name
     assert lib.spcies_cuda_solver_name().decode() == spec.options.solver_key()
-    assert lib.spcies_cuda_abi_version() == 1
+    assert lib.spcies_cuda_abi_version() == 2
+    if 'xrs' not in spec.extra_inputs:
+        assert hasattr(lib, spec.func_name + '_closed_loop')
     nn, mm, NN = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
     lib.spcies_cuda_dims(ctypes.byref(nn), ctypes.byref(mm), ctypes.byref(NN))
     assert (nn.value, mm.value, NN.value) == (spec.dims['n'], spec.dims['m'], spec.dims['N'])
@@ -73,7 +75,7 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     src = tmp_path / 'sz.c'
     fields_o = ['device', 'n_devices', 'arith', 'device_pointers', 'LB', 'UB', 'stream', 'block_threads', 'grid_blocks', 'tail_mode',
-                'tail_grace', 'engine', 'tail_caps', 'reserved']
+                'tail_grace', 'engine', 'tail_caps', 'warm_start', 'reserved', 'plant_AB']
     fields_i = ['kernel_ms', 'launches', 'sum_k', 'block_threads', 'n_devices', 'drain_us', 'parked', 'reserved']
     body = ''.join(f'printf("o {f} %zu\\n", offsetof(spcies_batch_opts, {f}));\n' for f in fields_o)
     body += ''.join(f'printf("i {f} %zu\\n", offsetof(spcies_batch_info, {f}));\n' for f in fields_i)

@@ -51,14 +51,16 @@ WORKLOADS = {
     # solvers added in round 2, at the reference tests' problem (N = 10) with the default tolerances
     'C6': ('C6_MPCT_ADMM_cs', 1 << 18, 1 << 12, 'MPCT ADMM_cs (extended state space) N=10, 256Ki-instance batch per GPU'),
     'C7': ('C7_HMPC_ADMM', 1 << 18, 1 << 12, 'HMPC ADMM (non-split, the toolbox default for HMPC) N=10, 256Ki-instance batch per GPU'),
+    'C8': ('C8_MPCT_ADMM_semiband', 1 << 18, 1 << 12, 'MPCT ADMM_semiband (banded + low-rank QP step) N=10, 256Ki-instance batch per GPU'),
 }
 # configurations measured next to the headline in the default run (2 timed steps each): `other_configs` of the JSON line
-OTHER_CONFIGS = ('C3', 'C3f', 'C4', 'C5a', 'C5b', 'C6', 'C7')
+OTHER_CONFIGS = ('C3', 'C3f', 'C4', 'C5a', 'C5b', 'C6', 'C7', 'C8')
 KERNELS = {'laxMPC_FISTA': 'spcies::fista::fista_mma_kernel', 'equMPC_ADMM': 'spcies::admm::admm_mma_kernel',
            'ellipMPC_ADMM_soc': 'spcies::soc::soc_mma_kernel', 'MPCT_EADMM': 'spcies::eadmm::eadmm_mma_kernel',
            'HMPC_SADMM_split': 'spcies::hmpc::hmpc_mma_kernel', 'HMPC_ADMM_split': 'spcies::hmpc::hmpc_mma_kernel',
            'MPCT_ADMM_cs': 'spcies::dense::dense_mma_kernel<mpct_cs::Engine>', 'HMPC_ADMM': 'spcies::dense::dense_mma_kernel<hmpc_ns::Engine>',
-           'ellipHMPC_ADMM': 'spcies::dense::dense_mma_kernel<hmpc_ns::Engine>'}
+           'ellipHMPC_ADMM': 'spcies::dense::dense_mma_kernel<hmpc_ns::Engine>',
+           'MPCT_ADMM_semiband': 'spcies::dense::dense_mma_kernel<mpct_sb::Engine>'}
 
 
 def fma_per_instance(solver_name, dims, sum_k, B, spec=None):
@@ -82,6 +84,16 @@ def fma_per_instance(solver_name, dims, sum_k, B, spec=None):
     if solver_name == 'MPCT_ADMM_cs':                            # the reference's sparse chain: nnz(AHi) + 2 nnz(L) + nnz(Hi) + nnz(HiA)
         nnz = sum(len(np.ravel(spec.const(c))) for c in ('AHi_val', 'Hi_val', 'HiA_val')) + 2 * len(np.ravel(spec.const('L_val')))
         return sum_k * nnz
+    if solver_name == 'MPCT_ADMM_semiband':
+        # the reference's three Woodbury-structured solves per iteration (code_MPCT_ADMM_semiband_C.c:191-770): 4 block-diagonal
+        # products, 2 M_hat + 2 U_hat sparse products, 2 banded Cholesky solves over N + 2 blocks, M_tilde / U_tilde, G and G'
+        blk = (N + 1) * (n * n + m * m)
+        mhat = 2 * ((N + 1) * (n * n + m * m))
+        uhat = N * (n * n + m * m)
+        chol = 2 * ((N + 2) * n * (n - 1) // 2 + (N + 1) * n * n)
+        mt = 2 * (n + m) * (N + 2) * n
+        gg = 2 * (N + 1) * n * (n + m)
+        return sum_k * (4 * blk + 2 * mhat + 2 * uhat + 2 * chol + 2 * mt + gg)
     if solver_name in ('HMPC_ADMM', 'ellipHMPC_ADMM'):           # dense M1, M2 + the two sparse products with C
         d = dims['dim']
         return sum_k * (d * d + d * n + len(np.ravel(spec.const('C_val'))) + len(np.ravel(spec.const('Ct_val'))))

@@ -257,8 +257,15 @@ def _sol_layout(header_text, save_name):
             pass
     body = re.search(r'typedef struct\s*\{(.*?)\}\s*sol_' + re.escape(save_name) + r'\s*;', header_text, flags=re.S)
     fields = []
+    seen = set()
     for fm in re.finditer(r'double\s+(\w+)\s*(?:\[(.*?)\])?\s*;', body.group(1)):
-        length = 1 if fm.group(2) is None else int(eval(fm.group(2), {'__builtins__': {}}, defs))
+        if fm.group(1) in seen:          # the other branch of an #if inside the struct (header_MPCT_ADMM_semiband_C.h:16-22)
+            continue
+        try:
+            length = 1 if fm.group(2) is None else int(eval(fm.group(2), {'__builtins__': {}}, defs))
+        except NameError:
+            continue
+        seen.add(fm.group(1))
         fields.append((fm.group(1), length))
     return fields
 

@@ -55,6 +55,11 @@ def reference_test(name: str, N: int = 10, masses: int = 3, forces=None, **solve
         param = dict(Q=Q, R=R, T=10.0 * Q, S=R, N=N)
         so = dict(rho_base=2.0, rho_mult=20.0, k_max=5000, tol=1e-7)
         kw = dict(formulation='MPCT', method='ADMM', submethod='cs')
+    elif name == 'MPCT_ADMM_semiband':
+        # no test of its own in the reference: the problem of tests/test_MPCT_ADMM.m with a penalty that converges (rho = 2)
+        param = dict(Q=Q, R=R, T=10.0 * Q, S=R, N=N)
+        so = dict(rho=2.0, k_max=5000, tol_p=1e-7, tol_d=1e-7)
+        kw = dict(formulation='MPCT', method='ADMM', submethod='semiband')
     elif name in ('HMPC_ADMM', 'ellipHMPC_ADMM'):
         # tests/test_HMPC_ADMM.m:6-22: method 'ADMM' with the default (empty) submethod = the non-split solver
         param = dict(Q=Q, R=R, N=N, w=3 * 1.627 * 0.2, Te=10.0 * N * Q, Se=R)
@@ -96,6 +101,7 @@ def bench_config(name: str):
         # round-2 solvers at the reference tests' problem, default tolerances (rho: the penalty that converges in O(100) iterations)
         'C6': ('MPCT_ADMM_cs', 10, dict(rho=2.0, tol=1e-4, k_max=1000)),
         'C7': ('HMPC_ADMM', 10, dict(rho=2.0, tol_p=1e-4, tol_d=1e-4, k_max=1000)),
+        'C8': ('MPCT_ADMM_semiband', 10, dict(rho=2.0, tol_p=1e-4, tol_d=1e-4, k_max=1000)),
     }
     solver, N, so = table[name]
     cfg = reference_test(solver, N=N, **so)

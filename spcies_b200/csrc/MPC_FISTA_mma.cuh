@@ -477,7 +477,7 @@ __global__ void __launch_bounds__(BLOCK, 1) fista_mma_kernel(const BatchIO io, c
                     stat_nc += (ef < 0);
                 }
                 live = false;
-                if (CL) cl_restart = cl_step + 1 < io.cl_steps;
+                if (CL) cl_restart = true;      // the sampling time is over: successor state, then the next one (if any) in place
             }
         }
         if constexpr (CL) {
@@ -500,8 +500,12 @@ __global__ void __launch_bounds__(BLOCK, 1) fista_mma_kernel(const BatchIO io, c
                             if (io.cl_x) io.cl_x[((long long)cl_step * io.cl_ld + inst) * n + xe[i]] = xnext[i];
                         }
                     }
-                    k = -1;
-                    live = true;
+                    if (cl_step < io.cl_steps) {
+                        k = -1;
+                        live = true;
+                    } else {
+                        cl_restart = false;                        // that was the last sampling time of this instance
+                    }
                 }
             }
         }

@@ -253,3 +253,104 @@ def cons_MPCT_ADMM_cs(recipe) -> SolverSpec:
         ref_header='formulations/+MPCT/header_MPCT_ADMM_cs_C.h',
         sol_fields=(('z', zlen), ('v', zlen), ('lambda', zlen)),
         vars=v, dims=dict(n=n, m=m, N=N, dim=zlen, n_eq=v['AHi_CSR'].nrow))
+
+
+# --------------------------------------------------------------------------------------
+# ADMM with the semi-banded (banded + low rank, Woodbury) equality-constrained QP step (submethod 'semiband')
+# --------------------------------------------------------------------------------------
+def compute_MPCT_ADMM_semiband_ingredients(recipe):
+    """formulations/+MPCT/compute_MPCT_ADMM_semiband_ingredients.m:20-365, scalar rho, hard constraints, no constrained output
+    (the defaults of def_options_MPCT_ADMM_semiband.m).  Decision vector z = (x_0, u_0, ..., x_{N-1}, u_{N-1}, x_s, u_s); the
+    Hessian is banded plus the 2 (n + m) columns / rows that couple every stage with (x_s, u_s); the z update applies the Woodbury
+    identity twice (to the Hessian and to the Schur complement of the equality constraints)."""
+    A, B, n, m, N = get_sys_param(recipe)
+    sys, param, opt = recipe.sys, recipe.param, recipe.options
+    solver = opt.solver
+    nm = n + m
+    if not np.isscalar(solver['rho']) or solver.get('force_vector_rho', False):
+        raise NotImplementedError('MPCT_ADMM_semiband: vector rho is not generated (scalar rho only)')
+    if solver.get('soft_constraints', False) or solver.get('constrained_output', False):
+        raise NotImplementedError('MPCT_ADMM_semiband: soft_constraints / constrained_output are not generated')
+    Q, R, T, S = (np.asarray(param[k], float) for k in ('Q', 'R', 'T', 'S'))
+    inf = float(opt.inf_value)
+    LBx = np.asarray(sys.get('LBx', -inf * np.ones(n)), float).ravel()
+    UBx = np.asarray(sys.get('UBx', inf * np.ones(n)), float).ravel()
+    LBu = np.asarray(sys.get('LBu', -inf * np.ones(m)), float).ravel()
+    UBu = np.asarray(sys.get('UBu', inf * np.ones(m)), float).ravel()
+    rho = float(solver['rho'])
+    QR = sla.block_diag(Q, R)
+    band = sla.block_diag(np.kron(np.eye(N), QR), sla.block_diag(N * Q + T, N * R + S))
+    H = band.copy()
+    H[:-nm, -nm:] = np.kron(np.ones((N, 1)), -QR)
+    H[-nm:, :-nm] = np.kron(np.ones((1, N)), -QR)
+    G = np.zeros(((N + 2) * n, (N + 1) * nm))
+    G[:n, :n] = np.eye(n)                                             # x_0 = x(t)
+    for l in range(N):                                                # x_{l+1} = A x_l + B u_l; the last one targets x_s
+        r0, c0 = (l + 1) * n, l * nm
+        G[r0:r0 + n, c0:c0 + nm + n] = np.hstack([A, B, -np.eye(n)])
+    G[-n:, -nm:] = np.hstack([A - np.eye(n), B])                      # (x_s, u_s) is an equilibrium
+    n_z = H.shape[0]
+    Gamma_hat = band + rho * np.eye(n_z)
+    Gamma_hat_inv = np.linalg.inv(Gamma_hat)
+    Y = np.kron(np.ones((N, 1)), -QR)
+    NNr, MM = Y.shape
+    U_hat = sla.block_diag(Y, np.eye(MM))
+    V_hat = np.block([[np.zeros((MM, NNr)), np.eye(MM)], [Y.T, np.zeros((MM, MM))]])
+    Gamma_tilde = G @ Gamma_hat_inv @ G.T
+    Gamma_tilde_inv = np.linalg.inv(Gamma_tilde)
+    U_tilde_full = -G @ Gamma_hat_inv @ U_hat @ np.linalg.inv(np.eye(2 * MM) + V_hat @ Gamma_hat_inv @ U_hat)
+    U_tilde = np.vstack([U_tilde_full[:2 * n, :], U_tilde_full[N * n:(N + 2) * n, :]])
+    V_tilde = V_hat @ Gamma_hat_inv @ G.T
+    M_hat = np.linalg.inv(np.eye(2 * nm) + V_hat @ Gamma_hat_inv @ U_hat) @ V_hat
+    M_hat_x1 = np.vstack([M_hat[:n, :n], M_hat[nm:nm + n, :n]])
+    M_hat_x2 = np.vstack([M_hat[:n, N * nm:N * nm + n], M_hat[nm:nm + n, N * nm:N * nm + n]])
+    M_hat_u1 = np.vstack([M_hat[n:nm, n:nm], M_hat[nm + n:2 * nm, n:nm]])
+    M_hat_u2 = np.vstack([M_hat[n:nm, N * nm + n:(N + 1) * nm], M_hat[nm + n:2 * nm, N * nm + n:(N + 1) * nm]])
+    M_tilde_full = np.linalg.inv(np.eye(2 * nm) + V_tilde @ Gamma_tilde_inv @ U_tilde_full) @ V_tilde
+    M_tilde = np.hstack([M_tilde_full[:, :2 * n], M_tilde_full[:, N * n:(N + 2) * n]])
+    v = dict(n=n, m=m, N=N, rho_is_scalar=True, A=A, B=B, Q=Q, R=R, T=T, S=S, G=G, H=H,
+             U_tilde=U_tilde, M_hat_x1=M_hat_x1, M_hat_x2=M_hat_x2, M_hat_u1=M_hat_u1, M_hat_u2=M_hat_u2, M_tilde=M_tilde,
+             LB=np.concatenate([LBx, LBu]), UB=np.concatenate([UBx, UBu]), rho=rho, rho_i=1.0 / rho,
+             Q_rho_i=np.linalg.inv(Q + rho * np.eye(n)), R_rho_i=np.linalg.inv(R + rho * np.eye(m)),
+             S_rho_i=np.linalg.inv(N * R + S + rho * np.eye(m)), T_rho_i=np.linalg.inv(N * Q + T + rho * np.eye(n)))
+    # blocks of the upper Cholesky factor of Gamma_tilde (N + 2 diagonal blocks with inverted diagonal, N + 1 super-diagonal ones;
+    # :347-363 -- the element-wise inversion of the diagonals is what `1/vars.Beta(i,i,:)` means there)
+    v['Alpha'], v['Beta'] = alpha_beta_from_chol(chol_upper(Gamma_tilde), n, N + 2)
+    v.update(scaling_vars(sys, n, m))
+    return v
+
+
+def cons_MPCT_ADMM_semiband(recipe) -> SolverSpec:
+    """formulations/+MPCT/cons_MPCT_ADMM_semiband_C.m:40-173."""
+    opts = recipe.options
+    v = compute_MPCT_ADMM_semiband_ingredients(recipe)
+    opts = opts.copy()
+    opts.force_diagonal = bool(isdiag(v['Q']) and isdiag(v['R']) and isdiag(v['T']) and isdiag(v['S']))
+    n, m, N = v['n'], v['m'], v['N']
+    vopt = var_options(opts)
+    prec = opts.precision
+    D = ('define',)
+    so = opts.solver
+    defs = default_defines(opts)
+    defs += [Row('SOFT_CONSTRAINTS', 0, True, 'bool', D), Row('CONSTRAINED_OUTPUT', 0, True, 'bool', D),
+             Row('nn_', n, True, 'uint', D), Row('mm_', m, True, 'uint', D), Row('nm_', n + m, True, 'uint', D),
+             Row('NN_', N, True, 'uint', D), Row('k_max', int(so['k_max']), True, 'uint', D),
+             Row('tol_p', float(so['tol_p']), True, 'float', D), Row('tol_d', float(so['tol_d']), True, 'float', D),
+             Row('eps_x', float(so['epsilon_x']), True, 'float', D), Row('eps_u', float(so['epsilon_u']), True, 'float', D),
+             Row('inf', float(opts.inf_value), True, 'float', D),
+             Row('SCALAR_RHO', 1, False, 'bool', D), Row('rho', v['rho'], True, prec, D), Row('rho_i', v['rho_i'], True, prec, D)]
+    consts = [Row(k, v[k], True, prec, vopt) for k in
+              ('LB', 'UB', 'Q', 'R', 'S', 'T', 'Q_rho_i', 'R_rho_i', 'S_rho_i', 'T_rho_i', 'A', 'B', 'Alpha', 'Beta', 'U_tilde',
+               'M_hat_x1', 'M_hat_x2', 'M_hat_u1', 'M_hat_u2', 'M_tilde')]
+    if opts.in_engineering:
+        consts += engineering_rows(v, prec, vopt)
+    zlen = (N + 1) * (n + m)
+    spec = SolverSpec(
+        formulation='MPCT', method='ADMM', submethod='semiband', func_name='MPCT_ADMM_semiband', kernel='MPCT_ADMM_semiband',
+        defines=defs, constants=consts,
+        ref_code='formulations/+MPCT/code_MPCT_ADMM_semiband_C.c',
+        ref_header='formulations/+MPCT/header_MPCT_ADMM_semiband_C.h',
+        sol_fields=(('z', zlen), ('v', zlen), ('lambda', zlen)),
+        vars=v, dims=dict(n=n, m=m, N=N, dim=zlen))
+    spec.options_override = opts
+    return spec

@@ -17,6 +17,7 @@ CONSTRUCTORS = {
     'ellipMPC_ADMM_soc': ellipMPC.cons_ellipMPC_ADMM_soc,
     'MPCT_EADMM': MPCT.cons_MPCT_EADMM,
     'MPCT_ADMM_cs': MPCT.cons_MPCT_ADMM_cs,
+    'MPCT_ADMM_semiband': MPCT.cons_MPCT_ADMM_semiband,
     'HMPC_ADMM': HMPC.cons_HMPC_ADMM,
     'ellipHMPC_ADMM': HMPC.cons_ellipHMPC_ADMM,
     'HMPC_ADMM_split': HMPC.cons_HMPC_ADMM_split,

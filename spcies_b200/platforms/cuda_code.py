@@ -43,6 +43,7 @@ KERNELS = {
     'ellipMPC_ADMM_soc': ('ellipMPC_ADMM_soc.cuh', {}),
     'MPCT_EADMM': ('MPCT_EADMM.cuh', {}),
     'MPCT_ADMM_cs': ('MPCT_ADMM_cs.cuh', {}),
+    'MPCT_ADMM_semiband': ('MPCT_ADMM_semiband.cuh', {}),
     'HMPC_ADMM_split': ('HMPC_ADMM_split.cuh', {}),
     'HMPC_ADMM': ('HMPC_ADMM.cuh', {'SPCIES_NREF': 1}),
     'ellipHMPC_ADMM': ('HMPC_ADMM.cuh', {'SPCIES_NREF': 3}),

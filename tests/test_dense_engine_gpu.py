@@ -12,7 +12,7 @@ from spcies_b200.solver import ARITH_EXACT, ARITH_FAST, ENGINE_MMA, ENGINE_SCALA
 pytestmark = pytest.mark.gpu
 
 # solver -> (golden vector of the reference's own test, sol field) or None
-SOLVERS = {'T_MPCT_ADMM_cs': ('MPCT_ADMM', 'z'), 'T_HMPC_ADMM': None, 'T_ellipHMPC_ADMM': None}
+SOLVERS = {'T_MPCT_ADMM_cs': ('MPCT_ADMM', 'z'), 'T_MPCT_ADMM_semiband': None, 'T_HMPC_ADMM': None, 'T_ellipHMPC_ADMM': None}
 
 
 def _inputs(sol, cfg, B, seed):

@@ -102,3 +102,44 @@ def test_hmpc_reference_against_independent_qp_solve(name, hmpc_qp):
     assert np.max(np.abs(z - hmpc_qp['z'])) <= 1e-4
     assert np.max(np.abs(hmpc_qp['G'] @ z - hmpc_qp['b'])) <= 1e-5       # dynamics + harmonic steady-state equalities
     assert np.allclose(u, hmpc_qp['z'][:2], atol=1e-5)
+
+
+def test_semiband_reference_against_the_mpct_golden_vector(golden):
+    """MPCT_ADMM_semiband has no test of its own in the reference; it solves the same MPCT problem as MPCT_ADMM_cs, whose golden
+    vector (tests/test_MPCT_ADMM.m:31, extended-state layout (x_j, x_s, u_j, u_s) per stage) therefore pins the restated semiband
+    ingredients: predicted states and inputs, artificial reference."""
+    ref, spec, cfg = _ref('T_MPCT_ADMM_semiband')
+    st = cfg['status']
+    u, k, e, sol = ref.solve(st['x'], st['xr'], st['ur'])
+    assert e == 1
+    n, m, N = spec.dims['n'], spec.dims['m'], spec.dims['N']
+    z = sol['z'].reshape(N + 1, n + m)                       # (x_0, u_0), ..., (x_{N-1}, u_{N-1}), (x_s, u_s)
+    zc = np.array(golden['MPCT_ADMM']['z_opt']).reshape(N, 2 * (n + m))
+    assert np.max(np.abs(z[:N, :n] - zc[:, :n])) <= 1e-4 and np.max(np.abs(z[:N, n:] - zc[:, 2 * n:2 * n + m])) <= 1e-4
+    assert np.max(np.abs(z[N, :n] - zc[0, n:2 * n])) <= 1e-4 and np.max(np.abs(z[N, n:] - zc[0, 2 * n + m:])) <= 1e-4
+    assert np.allclose(u, [0.8, 0.8], atol=1e-6)
+
+
+def test_semiband_qp_step_is_the_kkt_solve():
+    """One iteration from zero of the instantiated semiband template == the KKT solve of [H + rho I, G'; G, 0] [z; mu] = [-q; b]:
+    the identity the tensor-core engine of this solver is built on (csrc/MPCT_ADMM_semiband_mma.cuh)."""
+    from oracle import instantiate
+    from spcies_b200 import configs, make_spec
+    cfg = configs.reference_test('MPCT_ADMM_semiband', k_max=1)
+    spec = make_spec(cfg['sys'], cfg['param'], save_name='K1_MPCT_ADMM_semiband', **cfg['kw'])
+    if not instantiate.reference_available():
+        pytest.skip('needs the reference tree to instantiate a one-iteration solver')
+    ref = instantiate.make_reference(spec, 'ref_K1_MPCT_ADMM_semiband')
+    st = cfg['status']
+    u, k, e, sol = ref.solve(st['x'], st['xr'], st['ur'])
+    v = spec.vars
+    H, G, n, m, N = v['H'], v['G'], v['n'], v['m'], v['N']
+    L, LM = H.shape[0], G.shape[0]
+    K = np.block([[H + v['rho'] * np.eye(L), G.T], [G, np.zeros((LM, LM))]])
+    p = np.zeros(L)
+    p[N * (n + m):N * (n + m) + n] = -v['T'] @ st['xr']
+    p[N * (n + m) + n:] = -v['S'] @ st['ur']
+    b = np.zeros(LM)
+    b[:n] = st['x']
+    z = np.linalg.solve(K, np.concatenate([-p, b]))[:L]
+    assert k == 1 and np.max(np.abs(z - sol['z'])) <= 1e-10

@@ -15,12 +15,11 @@
 // element is loaded once per block and every row still accumulates in the reference's j order.
 //
 // This is the thread-per-instance formulation (state in shared memory or, for N = 50, in the L2-resident scratch; M1
-// read through the read-only path).  The batched product [M1] x [q_hat of a tile of instances] is GEMM shaped and is
-// the candidate for a tiled tensor/FP64-pipe kernel; see DESIGN.md "what comes next".
+// read through the read-only path): the EXACT / debug-payload path.  The FAST arithmetic runs the batched product
+// [M1] x [q_hat of a tile of instances] as a GEMM on the dense tensor-core engine (HMPC_ADMM_split_mma.cuh).
 #pragma once
 #include <type_traits>
-#include "spcies_kernel.cuh"
-#include "spcies_mma.cuh"
+#include "spcies_dense_mma.cuh"
 #include "spcies_sparse.cuh"
 
 #ifndef NON_SPARSE
@@ -204,53 +203,7 @@ struct Solver {
 
 #include "HMPC_ADMM_split_mma.cuh"
 
-// Host-side traits: the scalar skeleton plus the tensor-core engine (FAST arithmetic, no debug payload)
-struct Traits : PolicyTraits<Solver> {
-    typedef PolicyTraits<Solver> Base;
-    static size_t blob_bytes() { return HAS_MMA ? MMA_OFFSET + SMALL_BYTES + FRAG_BYTES : Base::blob_bytes(); }
-    static void fill_blob(void *dst) {
-        memset(dst, 0, blob_bytes());
-        Base::fill_blob(dst);
-        if constexpr (HAS_MMA) {
-            MmaSmall *S = new MmaSmall;
-            fill_mma_tables(spcies_h_consts, *S, reinterpret_cast<double2 *>((char *)dst + MMA_OFFSET + SMALL_BYTES));
-            memcpy((char *)dst + MMA_OFFSET, S, sizeof *S);
-            delete S;
-        }
-    }
-    static bool use_mma(int arith, const BatchIO &io) {
-        if constexpr (!HAS_MMA) return false;
-        return arith != SPCIES_CUDA_ARITH_EXACT && io.sol == nullptr && io.engine != SPCIES_CUDA_ENGINE_SCALAR && io.LB == nullptr;
-    }
-    static bool uses_scratch(int arith, const BatchIO &io) { return !use_mma(arith, io); }
-    static void engine_shape(int arith, const BatchIO &io, int &block, size_t &smem, int &ipb) {
-        ipb = block;
-        if (use_mma(arith, io)) {
-            block = MMA_BLOCK;
-            smem = MMA_SMEM;
-            ipb = MMA_IPB;
-        }
-    }
-    static cudaError_t launch(int arith, bool varb, int grid, int block, size_t smem, cudaStream_t s, const BatchIO &io,
-                              const void *dc, void *scratch) {
-        if (io.engine == SPCIES_CUDA_ENGINE_MMA && !use_mma(arith, io)) return cudaErrorNotSupported;
-        if constexpr (HAS_MMA) {
-            if (use_mma(arith, io)) {
-                cudaError_t e = cudaFuncSetAttribute(hmpc_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MMA_SMEM);
-                if (e != cudaSuccess) return e;
-                hmpc_mma_kernel<<<grid, MMA_BLOCK, MMA_SMEM, s>>>(io, (const unsigned char *)dc);
-                return cudaGetLastError();
-            }
-        }
-        return Base::launch(arith, varb, grid, block, smem, s, io, dc, scratch);
-    }
-    static cudaError_t attributes(int arith, bool varb, cudaFuncAttributes *a) {
-        if constexpr (HAS_MMA) {
-            if (arith != SPCIES_CUDA_ARITH_EXACT) return cudaFuncGetAttributes(a, hmpc_mma_kernel);
-        }
-        return Base::attributes(arith, varb, a);
-    }
-};
+typedef dense::DenseTraits<Solver, Engine> Traits;
 
 }  // namespace hmpc
 }  // namespace spcies

@@ -256,6 +256,7 @@ template <class E> __global__ void __launch_bounds__(Plan<E>::BLOCK, 1) dense_mm
                     live = true;
                 }
             }
+            if (TEAM > 1) team_sync();      // the ranks of a team initialise different tiles
         }
         // ---- input vector w (tiles split over the team)
 #pragma unroll 1

@@ -29,7 +29,7 @@ def gate(spec, u, k, e, ur_, kr, er, tol=1e-9, dk_max=1):
     same = k == kr
     conv = er == 1
     assert rel_err(u[same & conv], ur_[same & conv]) <= tol
-    assert rel_err(u[same & ~conv], ur_[same & ~conv]) <= 100 * tol
+    assert abs_err(u[same & ~conv], ur_[same & ~conv]) <= 100 * tol
     if (~same).any():
         stol = float(spec.define('tol', spec.define('tol_p')))
         assert abs_err(u[~same], ur_[~same]) <= 10 * stol

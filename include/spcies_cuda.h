@@ -170,6 +170,18 @@ const char *spcies_cuda_last_error(void);
                      int *e_flag, SOL *sol /* [B] or NULL */, const spcies_batch_opts *opts /* or NULL */,  \
                      spcies_batch_info *info /* or NULL */)
 
+/* TIME_VARYING solvers (options.time_varying, `#define TIME_VARYING 1`): the model is an argument -- A_in [nn_][nn_] and
+ * B_in [nn_][mm_] COLUMN-major (as MATLAB passes them), Q_in [nn_] and R_in [mm_] the diagonals of the weights, LB_in / UB_in [nm_]
+ * (code_laxMPC_FISTA_C.c:19, :101-137).  Batched: one model per instance, A [B][nn_*nn_], Bm [B][nn_*mm_], Q [B][nn_], R [B][mm_],
+ * LB / UB [B][nm_]; the block-Cholesky factorisation of every instance's W runs on the device (:139-262). */
+#define SPCIES_CUDA_DECLARE_SOLVER_TV(NAME, SOL)                                                           \
+    void NAME(double *x0_in, double *xr_in, double *ur_in, double *A_in, double *B_in, double *Q_in,       \
+              double *R_in, double *LB_in, double *UB_in, double *u_opt, int *k_in, int *e_flag, SOL *sol); \
+    int NAME##_batch(long B, const double *x0, const double *xr, const double *ur, const double *A,       \
+                     const double *Bm, const double *Q, const double *R, const double *LB, const double *UB, \
+                     double *u_opt, int *k, int *e_flag, SOL *sol /* [B] or NULL */,                       \
+                     const spcies_batch_opts *opts /* or NULL */, spcies_batch_info *info /* or NULL */)
+
 /* The solver families and the symbols each generated library exports (checked by tests/test_abi.py):
  *   SPCIES_CUDA_SOLVER(laxMPC_FISTA)       laxMPC_FISTA        laxMPC_FISTA_batch
  *   SPCIES_CUDA_SOLVER(laxMPC_ADMM)        laxMPC_ADMM         laxMPC_ADMM_batch

@@ -283,6 +283,7 @@ class RefSolver:
         self.n, self.m = spec.dims['n'], spec.dims['m']
         self.has_r = 'r_ellip' in spec.extra_inputs
         self.nref = 3 if 'xrs' in spec.extra_inputs else 1
+        self.tv = 'A_in' in spec.extra_inputs            # TIME_VARYING: per-instance model
         self.sol_len = sum(l for _, l in self.layout)
         self.lib.spcies_ref_sol_doubles.restype = ctypes.c_long
         assert self.lib.spcies_ref_sol_doubles() == self.sol_len, 'sol_<name> layout mismatch'
@@ -295,10 +296,24 @@ class RefSolver:
     def _p(a, t=ctypes.c_double):
         return None if a is None else a.ctypes.data_as(ctypes.POINTER(t))
 
-    def solve_batch(self, x0, xr, ur, r=None, threads=1, want_sol=False):
-        """Loop of single-instance reference calls (in C).  Returns ``u [B,m], k [B], e [B]`` (+ sol dict)."""
+    def solve_batch(self, x0, xr, ur, r=None, threads=1, want_sol=False, tv=None, LB=None, UB=None):
+        """Loop of single-instance reference calls (in C).  Returns ``u [B,m], k [B], e [B]`` (+ sol dict).
+        TIME_VARYING solvers: ``tv = (A [B,n,n], Bm [B,n,m], Q [B,n], R [B,m])`` (row-major matrices; passed column-major to the
+        reference, as MATLAB does) and ``LB / UB [B, nm]``."""
         x0 = np.ascontiguousarray(np.atleast_2d(x0), dtype=np.float64)
         B = x0.shape[0]
+        keep = []
+        if self.tv:
+            A_, B_, Q_, R_ = tv
+            Ac = np.ascontiguousarray(np.transpose(np.asarray(A_, float).reshape(B, self.n, self.n), (0, 2, 1)))
+            Bc = np.ascontiguousarray(np.transpose(np.asarray(B_, float).reshape(B, self.n, self.m), (0, 2, 1)))
+            Qc = np.ascontiguousarray(np.asarray(Q_, float).reshape(B, self.n))
+            Rc = np.ascontiguousarray(np.asarray(R_, float).reshape(B, self.m))
+            LBc = np.ascontiguousarray(np.asarray(LB, float).reshape(B, self.n + self.m))
+            UBc = np.ascontiguousarray(np.asarray(UB, float).reshape(B, self.n + self.m))
+            keep += [Ac, Bc, Qc, Rc, LBc, UBc]
+            self.lib.spcies_ref_set_refs(self._p(Ac), self._p(Bc), self._p(Qc), self._p(Rc))
+            self.lib.spcies_ref_set_bounds(self._p(LBc), self._p(UBc))
         if self.nref == 3:      # xr = (x_re, x_rs, x_rc), ur = (u_re, u_rs, u_rc)
             xs = [np.ascontiguousarray(np.atleast_2d(a), dtype=np.float64) for a in xr]
             us = [np.ascontiguousarray(np.atleast_2d(a), dtype=np.float64) for a in ur]

@@ -29,6 +29,9 @@ typedef struct {
     int *k, *e;
 } slice_t;
 
+static const double *g_bounds[2];   /* TIME_VARYING: LB, UB [B][nm_], set by spcies_ref_set_bounds() */
+void spcies_ref_set_bounds(const double *LB, const double *UB) { g_bounds[0] = LB; g_bounds[1] = UB; }
+
 long spcies_ref_sol_doubles(void) { return (long)(sizeof(SPCIES_SOL) / sizeof(double)); }
 
 static void *run_slice(void *arg) {
@@ -42,7 +45,17 @@ static void *run_slice(void *arg) {
         memcpy(xr, s->xr + i * nn_, sizeof xr);
         memcpy(ur, s->ur + i * mm_, sizeof ur);
         memset(&sol, 0, sizeof sol);
-#if SPCIES_NREF == 3
+#if TIME_VARYING == 1
+        /* per-instance model: A [nn_*nn_], B [nn_*mm_] column-major, Q [nn_], R [mm_], LB / UB [nm_] (code_laxMPC_FISTA_C.c:19) */
+        double Ai[nn_ * nn_], Bi[nn_ * mm_], Qi[nn_], Ri[mm_], LBi[nm_], UBi[nm_];
+        memcpy(Ai, s->xr2 + i * nn_ * nn_, sizeof Ai);
+        memcpy(Bi, s->xr3 + i * nn_ * mm_, sizeof Bi);
+        memcpy(Qi, s->ur2 + i * nn_, sizeof Qi);
+        memcpy(Ri, s->ur3 + i * mm_, sizeof Ri);
+        memcpy(LBi, g_bounds[0] + i * nm_, sizeof LBi);
+        memcpy(UBi, g_bounds[1] + i * nm_, sizeof UBi);
+        SPCIES_FUNC(x0, xr, ur, Ai, Bi, Qi, Ri, LBi, UBi, u, &k, &e, &sol);
+#elif SPCIES_NREF == 3
         double xr2[nn_], xr3[nn_], ur2[mm_], ur3[mm_];
         memcpy(xr2, s->xr2 + i * nn_, sizeof xr2);
         memcpy(xr3, s->xr3 + i * nn_, sizeof xr3);
@@ -92,7 +105,7 @@ int spcies_ref_batch(long B, const double *x0, const double *xr, const double *u
 /* Closed loop of reference calls for every instance (examples/cl_in_C/main_cl_in_C.c:100-117): u_t = solver(x_t), then the
  * successor state accumulated exactly like the example (x_aux[i] += AB[i][j] * x[j]; ... += AB[i][nn_+j] * u[j]).
  * x_traj [steps + 1][B][nn_], u_traj [steps][B][mm_], k_traj / e_traj [steps][B]; AB row-major [nn_][nn_ + mm_]. */
-#if SPCIES_NREF == 1
+#if SPCIES_NREF == 1 && TIME_VARYING != 1
 typedef struct {
     long lo, hi, B;
     int steps;

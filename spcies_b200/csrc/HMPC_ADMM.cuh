@@ -94,7 +94,7 @@ struct Solver {
                     b = A::nmsub(b, C->A[j][i], x0[i]);                                              // :85-90
                     qe = A::sub(qe, A::madd(A::mul(C->Te[j][i], xr[i]), C->QQ[j][i], x0[i]));        // :93-97
 #if SPCIES_NREF == 3
-                    qc = A::sub(qc, A::madd(A::mul(C->Th[j][i], (real)io.xr3[inst * n + i]), C->QQ[j][i], x0[i]));   // ellip :110-114
+                    qc = A::sub(qc, A::madd(A::mul(C->Th[j][i], (real)io.ex[1][inst * n + i]), C->QQ[j][i], x0[i]));   // ellip :110-114
 #else
                     qc = A::nmsub(qc, C->QQ[j][i], x0[i]);                                           // :98-102
 #endif
@@ -105,7 +105,7 @@ struct Solver {
 #if SPCIES_NREF == 3
                 real qs = real(0);
 #pragma unroll
-                for (int i = 0; i < n; ++i) qs = A::nmsub(qs, C->Th[j][i], (real)io.xr2[inst * n + i]);              // ellip :105-109
+                for (int i = 0; i < n; ++i) qs = A::nmsub(qs, C->Th[j][i], (real)io.ex[0][inst * n + i]);              // ellip :105-109
                 s.st(OFF_Q + n + j, qs);
 #endif
             }
@@ -119,8 +119,8 @@ struct Solver {
                 real q2 = real(0), q3 = real(0);
 #pragma unroll
                 for (int i = 0; i < m; ++i) {
-                    q2 = A::nmsub(q2, C->Sh[j][i], (real)io.ur2[inst * m + i]);                      // ellip :121-125
-                    q3 = A::nmsub(q3, C->Sh[j][i], (real)io.ur3[inst * m + i]);                      // ellip :126-130
+                    q2 = A::nmsub(q2, C->Sh[j][i], (real)io.ex[2][inst * m + i]);                      // ellip :121-125
+                    q3 = A::nmsub(q3, C->Sh[j][i], (real)io.ex[3][inst * m + i]);                      // ellip :126-130
                 }
                 s.st(OFF_Q + 3 * n + m + j, q2);
                 s.st(OFF_Q + 3 * n + 2 * m + j, q3);

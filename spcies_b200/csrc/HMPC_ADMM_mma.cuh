@@ -130,10 +130,10 @@ struct Engine {
                 else if (e < 2 * n) x = eng_x(C, io.xr, inst, n, e - n);
                 else if (e < 2 * n + m) x = eng_u(C, io.ur, inst, m, e - 2 * n);
 #if SPCIES_NREF == 3
-                else if (e < 3 * n + m) x = io.xr2[inst * n + e - 2 * n - m];
-                else if (e < 4 * n + m) x = io.xr3[inst * n + e - 3 * n - m];
-                else if (e < 4 * n + 2 * m) x = io.ur2[inst * m + e - 4 * n - m];
-                else if (e < 4 * n + 3 * m) x = io.ur3[inst * m + e - 4 * n - 2 * m];
+                else if (e < 3 * n + m) x = io.ex[0][inst * n + e - 2 * n - m];
+                else if (e < 4 * n + m) x = io.ex[1][inst * n + e - 3 * n - m];
+                else if (e < 4 * n + 2 * m) x = io.ex[2][inst * m + e - 4 * n - m];
+                else if (e < 4 * n + 3 * m) x = io.ex[3][inst * m + e - 4 * n - 2 * m];
 #endif
                 v[i] = x;
             }

@@ -712,6 +712,8 @@ struct Traits {
     static constexpr int NN = n, MM = m, NMM = nm;
     static constexpr bool HAS_R = false;
     static constexpr int NREF = 1;
+    static constexpr bool TV = false;
+    static constexpr int extra_width(int) { return 0; }
     static constexpr bool HAS_VARB = true;
     static constexpr bool HAS_PARK = true;                   // phase-1 / phase-2 launches (park & resume the slow tail)
     static constexpr int PARK_DOUBLES = fista::PARK_DOUBLES;

@@ -155,7 +155,10 @@ __device__ __forceinline__ void stage_constants(void *smem_dst, const void *gmem
 struct BatchIO {
     long long B;
     const double *x0, *xr, *ur, *r;   // [B][nn_], [B][nn_], [B][mm_], [B] (r: solvers with r_ellip only)
-    const double *xr2, *xr3, *ur2, *ur3;   // solvers with three references (ellipHMPC: xr = x_re, xr2 = x_rs, xr3 = x_rc; same for ur), else nullptr
+    // up to four extra per-instance inputs (widths Traits::extra_width(i)), else nullptr:
+    //   ellipHMPC (three references): ex[0] = x_rs, ex[1] = x_rc [B][nn_], ex[2] = u_rs, ex[3] = u_rc [B][mm_]
+    //   TIME_VARYING solvers: ex[0] = A [B][nn_*nn_], ex[1] = B [B][nn_*mm_] (column-major per instance), ex[2] = Q [B][nn_], ex[3] = R [B][mm_]
+    const double *ex[4];
     const double *LB, *UB;            // optional per-instance bounds [B][nm_], or nullptr
     double *u;                        // [B][mm_]
     int *k, *e;                       // [B]

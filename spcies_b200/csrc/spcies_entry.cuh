@@ -17,7 +17,8 @@ typedef Runtime<SPCIES_TRAITS> RT;
 // The reference's single-instance call = a batch of one.  Timing fields keep the reference's meaning and unit
 // (milliseconds, docs/timing.md:9-22): update_time = host->device, solve_time = kernel, polish_time = device->host.
 static inline void single_instance(double *x0_in, double *xr_in, double *ur_in, double *r_ellip, double *u_opt,
-                                   int *k_in, int *e_flag, SPCIES_SOL_T *sol, const double *const *extra = nullptr) {
+                                   int *k_in, int *e_flag, SPCIES_SOL_T *sol, const double *const *extra = nullptr,
+                                   const spcies_batch_opts *opts = nullptr) {
     spcies_batch_info info;
 #ifdef DEBUG
     SPCIES_SOL_T tmp;
@@ -28,7 +29,7 @@ static inline void single_instance(double *x0_in, double *xr_in, double *ur_in, 
 #else
                            nullptr,
 #endif
-                           nullptr, &info, extra);
+                           opts, &info, extra);
     if (rc != 0) {
         if (e_flag) *e_flag = SPCIES_CUDA_EFLAG_DEVICE;
         if (k_in) *k_in = 0;
@@ -86,7 +87,30 @@ int spcies_cuda_kernel_attributes(int arith, int *regs, int *smem_static, int *s
     return 0;
 }
 
-#if defined(SPCIES_NREF) && SPCIES_NREF == 3
+#if defined(TIME_VARYING) && TIME_VARYING == 1
+// per-instance model (options.time_varying): the reference signature of code_laxMPC_FISTA_C.c:19 -- A_in, B_in column-major,
+// Q_in, R_in the diagonals, LB_in / UB_in = [LBx; LBu] -- and its batched form (one model per instance)
+void SPCIES_FUNC(double *x0_in, double *xr_in, double *ur_in, double *A_in, double *B_in, double *Q_in, double *R_in, double *LB_in,
+                 double *UB_in, double *u_opt, int *k_in, int *e_flag, SPCIES_SOL_T *sol) {
+    const double *extra[4] = {A_in, B_in, Q_in, R_in};
+    spcies_batch_opts o;
+    memset(&o, 0, sizeof o);
+    o.LB = LB_in;
+    o.UB = UB_in;
+    ::spcies::single_instance(x0_in, xr_in, ur_in, nullptr, u_opt, k_in, e_flag, sol, extra, &o);
+}
+int SPCIES_CAT(SPCIES_FUNC, _batch)(long B, const double *x0, const double *xr, const double *ur, const double *A, const double *Bm,
+                                    const double *Q, const double *R, const double *LB, const double *UB, double *u_opt, int *k,
+                                    int *e_flag, SPCIES_SOL_T *sol, const spcies_batch_opts *opts, spcies_batch_info *info) {
+    const double *extra[4] = {A, Bm, Q, R};
+    spcies_batch_opts o;
+    memset(&o, 0, sizeof o);
+    if (opts) o = *opts;
+    o.LB = LB;
+    o.UB = UB;
+    return ::spcies::RT::get().run(B, x0, xr, ur, nullptr, u_opt, k, e_flag, reinterpret_cast<double *>(sol), &o, info, extra);
+}
+#elif defined(SPCIES_NREF) && SPCIES_NREF == 3
 // three references (x_re, x_rs, x_rc, u_re, u_rs, u_rc): header_ellipHMPC_ADMM_C.h:24
 void SPCIES_FUNC(double *x0_in, double *xre_in, double *xrs_in, double *xrc_in, double *ure_in, double *urs_in, double *urc_in,
                  double *u_opt, int *k_in, int *e_flag, SPCIES_SOL_T *sol) {

@@ -62,7 +62,7 @@ struct DeviceCtx {
     // device staging buffers (grown on demand)
     long long cap = 0, cap_sol = 0, cap_b = 0;
     double *d_x0 = nullptr, *d_xr = nullptr, *d_ur = nullptr, *d_r = nullptr, *d_LB = nullptr, *d_UB = nullptr;
-    double *d_xr2 = nullptr, *d_xr3 = nullptr, *d_ur2 = nullptr, *d_ur3 = nullptr;   // Traits::NREF == 3 (ellipHMPC)
+    double *d_ex[4] = {nullptr, nullptr, nullptr, nullptr};   // extra per-instance inputs (Traits::extra_width: ellipHMPC, TIME_VARYING)
     double *d_u = nullptr, *d_sol = nullptr;
     int *d_k = nullptr, *d_e = nullptr;
     void *d_scratch = nullptr;   // per-instance state of solvers whose iterates do not fit shared memory
@@ -165,12 +165,8 @@ template <class Traits> struct Runtime {
             if ((rc = grow(&c.d_xr, n * Traits::NN))) return rc;
             if ((rc = grow(&c.d_ur, n * Traits::MM))) return rc;
             if (Traits::HAS_R && (rc = grow(&c.d_r, n))) return rc;
-            if (Traits::NREF == 3) {
-                if ((rc = grow(&c.d_xr2, n * Traits::NN))) return rc;
-                if ((rc = grow(&c.d_xr3, n * Traits::NN))) return rc;
-                if ((rc = grow(&c.d_ur2, n * Traits::MM))) return rc;
-                if ((rc = grow(&c.d_ur3, n * Traits::MM))) return rc;
-            }
+            for (int i = 0; i < 4; ++i)
+                if (Traits::extra_width(i) > 0 && (rc = grow(&c.d_ex[i], n * Traits::extra_width(i)))) return rc;
             if ((rc = grow(&c.d_u, n * Traits::MM))) return rc;
             if ((rc = grow(&c.d_k, n))) return rc;
             if ((rc = grow(&c.d_e, n))) return rc;
@@ -198,7 +194,7 @@ template <class Traits> struct Runtime {
             cudaSetDevice(c.dev);
             cudaFree(c.d_consts); cudaFree(c.d_queue);
             cudaFree(c.d_x0); cudaFree(c.d_xr); cudaFree(c.d_ur); cudaFree(c.d_r); cudaFree(c.d_LB); cudaFree(c.d_UB);
-            cudaFree(c.d_xr2); cudaFree(c.d_xr3); cudaFree(c.d_ur2); cudaFree(c.d_ur3);
+            for (auto p_ : c.d_ex) cudaFree(p_);
             cudaFree(c.d_clx); cudaFree(c.d_clu); cudaFree(c.d_clk); cudaFree(c.d_cle); cudaFree(c.d_plant);
             cudaFree(c.d_u); cudaFree(c.d_sol); cudaFree(c.d_k); cudaFree(c.d_e); cudaFree(c.d_scratch); cudaFree(c.d_park); cudaFree(c.d_park2);
             for (auto &e : c.ev) cudaEventDestroy(e);
@@ -213,7 +209,7 @@ template <class Traits> struct Runtime {
     struct Call {
         long long B;
         const double *x0, *xr, *ur, *r, *LB, *UB;
-        const double *xr2 = nullptr, *xr3 = nullptr, *ur2 = nullptr, *ur3 = nullptr;
+        const double *ex[4] = {nullptr, nullptr, nullptr, nullptr};
         double *u;
         int *k, *e;
         double *sol;
@@ -247,7 +243,8 @@ template <class Traits> struct Runtime {
     // seven copies.  Same kernels, same results.
     static constexpr long long SMALL_B = 64;
     static constexpr size_t stage_doubles() {
-        return (size_t)SMALL_B * (2 * Traits::NN + 2 * Traits::MM + 1 + 2 * Traits::NMM + 1 + (Traits::NREF == 3 ? 2 * Traits::NN + 2 * Traits::MM : 0));
+        return (size_t)SMALL_B * (2 * Traits::NN + 2 * Traits::MM + 1 + 2 * Traits::NMM + 1 + Traits::extra_width(0) + Traits::extra_width(1) +
+                                  Traits::extra_width(2) + Traits::extra_width(3));
     }
     int run_small(DeviceCtx &c, const Call &cl, Result &res) {
         const long long B = cl.B;
@@ -260,18 +257,16 @@ template <class Traits> struct Runtime {
         double *h = c.h_stage, *d = c.d_stage;
         const size_t o_x0 = 0, o_xr = o_x0 + SMALL_B * Traits::NN, o_ur = o_xr + SMALL_B * Traits::NN, o_r = o_ur + SMALL_B * Traits::MM,
                      o_lb = o_r + SMALL_B, o_ub = o_lb + SMALL_B * Traits::NMM, o_u = o_ub + SMALL_B * Traits::NMM,
-                     o_ke = o_u + SMALL_B * Traits::MM, o_x2 = o_ke + SMALL_B, o_x3 = o_x2 + SMALL_B * Traits::NN,
-                     o_u2 = o_x3 + SMALL_B * Traits::NN, o_u3 = o_u2 + SMALL_B * Traits::MM;
+                     o_ke = o_u + SMALL_B * Traits::MM;
+        size_t o_ex[4];
+        o_ex[0] = o_ke + SMALL_B;
+        for (int i = 1; i < 4; ++i) o_ex[i] = o_ex[i - 1] + SMALL_B * Traits::extra_width(i - 1);
         memcpy(h + o_x0, cl.x0, (size_t)B * Traits::NN * 8);
         memcpy(h + o_xr, cl.xr, (size_t)B * Traits::NN * 8);
         memcpy(h + o_ur, cl.ur, (size_t)B * Traits::MM * 8);
         if (Traits::HAS_R) memcpy(h + o_r, cl.r, (size_t)B * 8);
-        if (Traits::NREF == 3) {
-            memcpy(h + o_x2, cl.xr2, (size_t)B * Traits::NN * 8);
-            memcpy(h + o_x3, cl.xr3, (size_t)B * Traits::NN * 8);
-            memcpy(h + o_u2, cl.ur2, (size_t)B * Traits::MM * 8);
-            memcpy(h + o_u3, cl.ur3, (size_t)B * Traits::MM * 8);
-        }
+        for (int i = 0; i < 4; ++i)
+            if (Traits::extra_width(i) > 0) memcpy(h + o_ex[i], cl.ex[i], (size_t)B * Traits::extra_width(i) * 8);
         if (varb) {
             memcpy(h + o_lb, cl.LB, (size_t)B * Traits::NMM * 8);
             memcpy(h + o_ub, cl.UB, (size_t)B * Traits::NMM * 8);
@@ -281,7 +276,7 @@ template <class Traits> struct Runtime {
         io.B = B;
         io.queue = c.d_queue;
         io.x0 = d + o_x0; io.xr = d + o_xr; io.ur = d + o_ur; io.r = d + o_r;
-        if (Traits::NREF == 3) { io.xr2 = d + o_x2; io.xr3 = d + o_x3; io.ur2 = d + o_u2; io.ur3 = d + o_u3; }
+        for (int i = 0; i < 4; ++i) io.ex[i] = Traits::extra_width(i) > 0 ? d + o_ex[i] : nullptr;
         io.LB = varb ? d + o_lb : nullptr; io.UB = varb ? d + o_ub : nullptr;
         io.u = d + o_u;
         io.k = reinterpret_cast<int *>(d + o_ke);
@@ -344,12 +339,12 @@ template <class Traits> struct Runtime {
         io.queue = c.d_queue;
         if (cl.device_pointers) {
             io.x0 = cl.x0; io.xr = cl.xr; io.ur = cl.ur; io.r = cl.r; io.LB = cl.LB; io.UB = cl.UB;
-            io.xr2 = cl.xr2; io.xr3 = cl.xr3; io.ur2 = cl.ur2; io.ur3 = cl.ur3;
+            for (int i = 0; i < 4; ++i) io.ex[i] = cl.ex[i];
             io.u = cl.u; io.k = cl.k; io.e = cl.e; io.sol = cl.sol;
         } else {
             if ((rc = reserve(c, B, varb, cl.sol != nullptr))) return rc;
             io.x0 = c.d_x0; io.xr = c.d_xr; io.ur = c.d_ur; io.r = c.d_r;
-            if (Traits::NREF == 3) { io.xr2 = c.d_xr2; io.xr3 = c.d_xr3; io.ur2 = c.d_ur2; io.ur3 = c.d_ur3; }
+            for (int i = 0; i < 4; ++i) io.ex[i] = Traits::extra_width(i) > 0 ? c.d_ex[i] : nullptr;
             io.LB = varb ? c.d_LB : nullptr; io.UB = varb ? c.d_UB : nullptr;
             io.u = c.d_u; io.k = c.d_k; io.e = c.d_e; io.sol = cl.sol ? c.d_sol : nullptr;
             // results straight into the caller's arrays when those are pinned (device-mapped) host memory: 24 bytes per instance
@@ -443,11 +438,9 @@ template <class Traits> struct Runtime {
                 SPCIES_CK(cudaMemcpyAsync(c.d_xr + lo * Traits::NN, cl.xr + lo * Traits::NN, cnt * Traits::NN * 8, cudaMemcpyHostToDevice, cs));
                 SPCIES_CK(cudaMemcpyAsync(c.d_ur + lo * Traits::MM, cl.ur + lo * Traits::MM, cnt * Traits::MM * 8, cudaMemcpyHostToDevice, cs));
                 if (Traits::HAS_R) SPCIES_CK(cudaMemcpyAsync(c.d_r + lo, cl.r + lo, cnt * 8, cudaMemcpyHostToDevice, cs));
-                if (Traits::NREF == 3) {
-                    SPCIES_CK(cudaMemcpyAsync(c.d_xr2 + lo * Traits::NN, cl.xr2 + lo * Traits::NN, cnt * Traits::NN * 8, cudaMemcpyHostToDevice, cs));
-                    SPCIES_CK(cudaMemcpyAsync(c.d_xr3 + lo * Traits::NN, cl.xr3 + lo * Traits::NN, cnt * Traits::NN * 8, cudaMemcpyHostToDevice, cs));
-                    SPCIES_CK(cudaMemcpyAsync(c.d_ur2 + lo * Traits::MM, cl.ur2 + lo * Traits::MM, cnt * Traits::MM * 8, cudaMemcpyHostToDevice, cs));
-                    SPCIES_CK(cudaMemcpyAsync(c.d_ur3 + lo * Traits::MM, cl.ur3 + lo * Traits::MM, cnt * Traits::MM * 8, cudaMemcpyHostToDevice, cs));
+                for (int i = 0; i < 4; ++i) {
+                    const int w = Traits::extra_width(i);
+                    if (w > 0) SPCIES_CK(cudaMemcpyAsync(c.d_ex[i] + lo * w, cl.ex[i] + lo * w, cnt * w * 8, cudaMemcpyHostToDevice, cs));
                 }
                 if (varb) {
                     SPCIES_CK(cudaMemcpyAsync(c.d_LB + lo * Traits::NMM, cl.LB + lo * Traits::NMM, cnt * Traits::NMM * 8, cudaMemcpyHostToDevice, cs));
@@ -647,7 +640,7 @@ template <class Traits> struct Runtime {
         if (opts) o = *opts;
         if (B < 0 || steps < 0) return fail(SPCIES_CUDA_EINVAL, "B < 0 or steps < 0");
         if (o.warm_start < 0 || o.warm_start > 2) return fail(SPCIES_CUDA_EINVAL, "warm_start must be 0, 1 or 2");
-        if (Traits::NREF != 1) return fail(SPCIES_CUDA_EUNSUPPORTED, "closed loop: not available for solvers with three references");
+        if (Traits::extra_width(0) > 0) return fail(SPCIES_CUDA_EUNSUPPORTED, "closed loop: not available for solvers with extra inputs");
         if (B > 0 && steps > 0 && (!x0 || !xr || !ur || !u_traj || !k_traj || !e_traj || (Traits::HAS_R && !r)))
             return fail(SPCIES_CUDA_EINVAL, "NULL array argument");
         if (o.device_pointers || o.LB || o.UB) return fail(SPCIES_CUDA_EUNSUPPORTED, "closed loop: host arrays, generated bounds");
@@ -716,7 +709,8 @@ template <class Traits> struct Runtime {
         return 0;
     }
 
-    // extra: the four additional reference arrays {x_rs, x_rc, u_rs, u_rc} of solvers with Traits::NREF == 3, else nullptr
+    // extra: the four additional per-instance inputs of solvers with Traits::extra_width(i) > 0 (ellipHMPC: x_rs, x_rc, u_rs, u_rc;
+    // TIME_VARYING: A, B, Q, R), else nullptr
     int run(long long B, const double *x0, const double *xr, const double *ur, const double *r, double *u, int *k,
             int *e, double *sol, const spcies_batch_opts *opts, spcies_batch_info *info, const double *const *extra = nullptr) {
         auto t0 = std::chrono::steady_clock::now();
@@ -726,8 +720,9 @@ template <class Traits> struct Runtime {
         if (B < 0) return fail(SPCIES_CUDA_EINVAL, "B < 0");
         if (B > 0 && (!x0 || !xr || !ur || !u || !k || !e || (Traits::HAS_R && !r)))
             return fail(SPCIES_CUDA_EINVAL, "NULL array argument");
-        if (B > 0 && Traits::NREF == 3 && (!extra || !extra[0] || !extra[1] || !extra[2] || !extra[3]))
-            return fail(SPCIES_CUDA_EINVAL, "NULL reference array argument");
+        if (B > 0 && Traits::extra_width(0) > 0 && (!extra || !extra[0] || !extra[1] || !extra[2] || !extra[3]))
+            return fail(SPCIES_CUDA_EINVAL, "NULL array argument (references / model)");
+        if (B > 0 && Traits::TV && (!o.LB || !o.UB)) return fail(SPCIES_CUDA_EINVAL, "a TIME_VARYING solver needs LB and UB");
         if ((o.LB == nullptr) != (o.UB == nullptr)) return fail(SPCIES_CUDA_EINVAL, "LB and UB must be given together");
         if (o.arith != SPCIES_CUDA_ARITH_FAST && o.arith != SPCIES_CUDA_ARITH_EXACT)
             return fail(SPCIES_CUDA_EINVAL, "unknown arith mode");
@@ -749,10 +744,8 @@ template <class Traits> struct Runtime {
             c.B = hi - lo;
             c.x0 = x0 + lo * Traits::NN; c.xr = xr + lo * Traits::NN; c.ur = ur + lo * Traits::MM;
             c.r = r ? r + lo : nullptr;
-            if (Traits::NREF == 3 && extra) {
-                c.xr2 = extra[0] + lo * Traits::NN; c.xr3 = extra[1] + lo * Traits::NN;
-                c.ur2 = extra[2] + lo * Traits::MM; c.ur3 = extra[3] + lo * Traits::MM;
-            }
+            for (int i = 0; i < 4; ++i)
+                if (Traits::extra_width(i) > 0 && extra) c.ex[i] = extra[i] + lo * Traits::extra_width(i);
             c.LB = o.LB ? o.LB + lo * Traits::NMM : nullptr; c.UB = o.UB ? o.UB + lo * Traits::NMM : nullptr;
             c.u = u + lo * Traits::MM; c.k = k + lo; c.e = e + lo;
             c.sol = sol ? sol + lo * (long long)Traits::SOL_DOUBLES : nullptr;
@@ -795,7 +788,8 @@ template <class Traits> struct Runtime {
             info->n_devices = ndev;
             if (!o.device_pointers) {
                 const long long varb = (o.LB ? 2LL * Traits::NMM : 0);
-                info->h2d_bytes = B * 8 * (2 * Traits::NN + Traits::MM + (Traits::HAS_R ? 1 : 0) + varb + (Traits::NREF == 3 ? 2 * Traits::NN + 2 * Traits::MM : 0));
+                info->h2d_bytes = B * 8 * (2 * Traits::NN + Traits::MM + (Traits::HAS_R ? 1 : 0) + varb + Traits::extra_width(0) + Traits::extra_width(1) +
+                                           Traits::extra_width(2) + Traits::extra_width(3));
                 info->d2h_bytes = B * (8 * Traits::MM + 8) + (sol ? B * 8LL * Traits::SOL_DOUBLES : 0);
             }
             static int regs_cache[2][2] = {{0, 0}, {0, 0}};          // cudaFuncGetAttributes costs microseconds: once per variant

@@ -120,6 +120,17 @@ template <class S> struct PolicyTraits {
 #else
     static constexpr int NREF = 1;
 #endif
+#if defined(TIME_VARYING) && TIME_VARYING == 1
+    static constexpr bool TV = true;       // per-instance model: extra inputs A, B, Q, R (and LB, UB through opts)
+#else
+    static constexpr bool TV = false;
+#endif
+    // widths of the extra per-instance inputs BatchIO::ex[i] (0: unused)
+    static constexpr int extra_width(int i) {
+        if (TV) return i == 0 ? nn_ * nn_ : (i == 1 ? nn_ * mm_ : (i == 2 ? nn_ : mm_));
+        if (NREF == 3) return i < 2 ? nn_ : mm_;
+        return 0;
+    }
     static constexpr bool HAS_VARB = S::HAS_VARB;
     static constexpr int SOL_DOUBLES = (int)(sizeof(SPCIES_SOL_T) / sizeof(double));
     typedef spcies_consts Consts;

@@ -115,6 +115,7 @@ def _cons_FISTA(recipe, terminal: bool) -> SolverSpec:
         ref_code=f'formulations/+{name}/code_{name}_FISTA_C.c',
         ref_header=f'formulations/+{name}/header_{name}_FISTA_C.h',
         sol_fields=(('z', zlen), ('lambda', N * n)),
+        extra_inputs=('A_in', 'B_in', 'Q_in', 'R_in', 'LB_in', 'UB_in') if opts.time_varying else (),
         vars=v, dims=dict(n=n, m=m, N=N))
 
 

@@ -50,6 +50,12 @@ KERNELS = {
 }
 
 
+# solvers generated with options.time_varying (per-instance model, factorisation on the device)
+KERNELS_TV = {
+    'laxMPC_FISTA': ('MPC_FISTA_tv.cuh', {'SPCIES_TERMINAL': 1}),
+}
+
+
 def write_value(value, is_int=False, is_bool=False):
     """Number formats of dec_var.m:241-265 (ints ``%d``, reals ``%1.15f``, +-inf -> +-1e20)."""
     v = float(value)
@@ -105,6 +111,10 @@ def emit_text(spec, save_name):
     if key not in KERNELS:
         raise NotImplementedError(f'no CUDA kernel template for {key}')
     kernel_hdr, switches = KERNELS[key]
+    if opts.time_varying:
+        if key not in KERNELS_TV:
+            raise NotImplementedError(f'time_varying: no CUDA kernel template for {key} (available: {sorted(KERNELS_TV)})')
+        kernel_hdr, switches = KERNELS_TV[key]
     sol_t = f'sol_{save_name}'
     has_r = 1 if 'r_ellip' in spec.extra_inputs else 0
 
@@ -121,6 +131,8 @@ def emit_text(spec, save_name):
     macro = 'SPCIES_CUDA_DECLARE_SOLVER_R' if has_r else 'SPCIES_CUDA_DECLARE_SOLVER'
     if 'xrs' in spec.extra_inputs:
         macro = 'SPCIES_CUDA_DECLARE_SOLVER_6REF'
+    if opts.time_varying:
+        macro = 'SPCIES_CUDA_DECLARE_SOLVER_TV'
     h += [f'{macro}({spec.func_name}, {sol_t});', '#ifdef __cplusplus', '}', '#endif', '', '#endif', '',
           '// This code is generated by the CUDA platform of spcies_b200 for the Spcies toolbox: '
           'https://github.com/GepocUS/Spcies', '']
@@ -177,11 +189,27 @@ def nvcc_path():
     return p if os.path.exists(p) else None
 
 
+def _included_headers(path, seen=None):
+    """The .cuh / .h files under csrc/ that ``path`` includes, transitively (so that a new kernel header does not invalidate
+    the build stamp of every other generated solver)."""
+    import re
+    seen = set() if seen is None else seen
+    try:
+        text = open(path).read()
+    except OSError:
+        return seen
+    for inc in re.findall(r'^\s*#\s*include\s+"([^"]+)"', text, flags=re.M):
+        q = os.path.join(CSRC_DIR, inc)
+        if os.path.exists(q) and q not in seen:
+            seen.add(q)
+            _included_headers(q, seen)
+    return seen
+
+
 def _sources_digest(cu_path, extra_flags):
     h = hashlib.sha256()
     h.update(' '.join(NVCC_ARCH + NVCC_FLAGS + list(extra_flags)).encode())
-    for p in [cu_path, cu_path[:-3] + '.h', os.path.join(INCLUDE_DIR, 'spcies_cuda.h')] + \
-            sorted(os.path.join(CSRC_DIR, f) for f in os.listdir(CSRC_DIR) if f.endswith('.cuh')):
+    for p in [cu_path, cu_path[:-3] + '.h', os.path.join(INCLUDE_DIR, 'spcies_cuda.h')] + sorted(_included_headers(cu_path)):
         with open(p, 'rb') as f:
             h.update(f.read())
     return h.hexdigest()

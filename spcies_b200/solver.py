@@ -70,6 +70,8 @@ class CudaSolver:
         self.has_r = hasattr(L, 'ellipMPC_ADMM_soc')
         # three references (x_re, x_rs, x_rc) / (u_re, u_rs, u_rc): ellipHMPC, header_ellipHMPC_ADMM_C.h:24
         self.nref = 3 if (spec is not None and 'xrs' in spec.extra_inputs) else 1
+        # TIME_VARYING solvers take the model per call / per instance: A, B (column-major), Q, R, LB, UB (code_laxMPC_FISTA_C.c:19)
+        self.tv = spec is not None and 'A_in' in spec.extra_inputs
         self._single = getattr(L, self.func_name)
         self._single.restype = None
         self._batch = getattr(L, self.func_name + '_batch')
@@ -114,7 +116,20 @@ class CudaSolver:
         return out
 
     # ------------------------------------------------------------------------------------------
-    def solve(self, x0, xr, ur, r=None):
+    def _tv_args(self, tv, LB, UB, B):
+        """(A, Bm, Q, R) row-major per instance -> the column-major arrays of the reference signature, + LB / UB."""
+        if tv is None or LB is None or UB is None:
+            raise ValueError('a TIME_VARYING solver needs tv = (A, B, Q, R) and LB, UB')
+        A_, B_, Q_, R_ = tv
+        Ac = np.ascontiguousarray(np.transpose(np.asarray(A_, dtype=np.float64).reshape(B, self.n, self.n), (0, 2, 1)))
+        Bc = np.ascontiguousarray(np.transpose(np.asarray(B_, dtype=np.float64).reshape(B, self.n, self.m), (0, 2, 1)))
+        Qc = np.ascontiguousarray(np.asarray(Q_, dtype=np.float64).reshape(B, self.n))
+        Rc = np.ascontiguousarray(np.asarray(R_, dtype=np.float64).reshape(B, self.m))
+        LBc = np.ascontiguousarray(np.asarray(LB, dtype=np.float64).reshape(B, self.n + self.m))
+        UBc = np.ascontiguousarray(np.asarray(UB, dtype=np.float64).reshape(B, self.n + self.m))
+        return [Ac, Bc, Qc, Rc, LBc, UBc]
+
+    def solve(self, x0, xr, ur, r=None, tv=None, LB=None, UB=None):
         """Single instance through the reference's own symbol and signature."""
         x0 = np.ascontiguousarray(x0, dtype=np.float64).ravel().copy()
         xrs = [np.ascontiguousarray(a, dtype=np.float64).ravel().copy() for a in (xr if self.nref == 3 else [xr])]
@@ -126,6 +141,9 @@ class CudaSolver:
         k, e = c_int(0), c_int(0)
         sol = np.zeros(self.sol_doubles)
         args = [_dptr(x0)] + [_dptr(a) for a in xrs] + [_dptr(a) for a in urs]
+        if self.tv:
+            tva = self._tv_args(tv, LB, UB, 1)
+            args += [_dptr(a) for a in tva]
         if self.has_r:
             if r is None:
                 raise ValueError('this solver takes the size of the terminal ellipsoid: r is required')
@@ -138,7 +156,8 @@ class CudaSolver:
         return u, k.value, e.value, self._split_sol(sol)
 
     def solve_batch(self, x0, xr, ur, r=None, LB=None, UB=None, arith=ARITH_FAST, device=0, n_devices=1,
-                    want_sol=False, out=None, block_threads=0, grid_blocks=0, tail_mode=0, tail_grace=0, engine=0, tail_caps=()):
+                    want_sol=False, out=None, block_threads=0, grid_blocks=0, tail_mode=0, tail_grace=0, engine=0, tail_caps=(),
+                    tv=None):
         """B instances through ``<func>_batch``.  Arrays are ``[B, n]`` / ``[B, m]`` (instance-major)."""
         x0 = np.ascontiguousarray(x0, dtype=np.float64)
         xrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (xr if self.nref == 3 else [xr])]
@@ -167,6 +186,10 @@ class CudaSolver:
         for i, c in enumerate(tuple(tail_caps)[:3]):
             opts.tail_caps[i] = int(c)
         keep = []
+        tva = None
+        if self.tv:
+            tva = self._tv_args(tv, LB, UB, B)
+            LB = UB = None                    # they travel in the argument list of a TIME_VARYING solver
         if LB is not None or UB is not None:
             LB = np.ascontiguousarray(LB, dtype=np.float64)
             UB = np.ascontiguousarray(UB, dtype=np.float64)
@@ -176,6 +199,8 @@ class CudaSolver:
             keep += [LB, UB]
         info = BatchInfo()
         args = [c_long(B), _dptr(x0)] + [_dptr(a) for a in xrs] + [_dptr(a) for a in urs]
+        if tva is not None:
+            args += [_dptr(a) for a in tva]
         if self.has_r:
             rr = np.ascontiguousarray(np.broadcast_to(np.asarray(r, dtype=np.float64).ravel(), (B,)))
             keep.append(rr)

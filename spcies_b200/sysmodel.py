@@ -136,3 +136,19 @@ def synthetic_batch(sys, B, seed=0, with_r=False, chunk=1 << 20):
     if with_r:
         out["r"] = r
     return out
+
+
+def perturbed_models(sys, param, B, seed=0, rel=0.03):
+    """Per-instance models for the TIME_VARYING solvers: ``A_i, B_i`` = the nominal model with every entry perturbed by up to
+    ``rel`` (relative), ``Q_i, R_i`` = the nominal diagonal weights scaled by U[0.5, 2], bounds with the position upper bounds in
+    U[0.25, 0.35].  Returns ``(A [B,n,n], Bm [B,n,m], Q [B,n], R [B,m]), LB [B,nm], UB [B,nm]``."""
+    rng = np.random.default_rng(seed)
+    n, m, p = sys['n'], sys['m'], sys['p']
+    A = sys['A'][None] * (1.0 + rel * rng.uniform(-1, 1, (B, n, n)))
+    Bm = sys['B'][None] * (1.0 + rel * rng.uniform(-1, 1, (B, n, m)))
+    Q = np.diag(param['Q'])[None] * rng.uniform(0.5, 2.0, (B, n))
+    R = np.diag(param['R'])[None] * rng.uniform(0.5, 2.0, (B, m))
+    LB = np.tile(np.concatenate([sys['LBx'], sys['LBu']]), (B, 1))
+    UB = np.tile(np.concatenate([sys['UBx'], sys['UBu']]), (B, 1))
+    UB[:, :p] = rng.uniform(0.25, 0.35, (B, p))
+    return (np.ascontiguousarray(A), np.ascontiguousarray(Bm), Q, R), LB, UB

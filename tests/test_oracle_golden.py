@@ -143,3 +143,23 @@ def test_semiband_qp_step_is_the_kkt_solve():
     b[:n] = st['x']
     z = np.linalg.solve(K, np.concatenate([-p, b]))[:L]
     assert k == 1 and np.max(np.abs(z - sol['z'])) <= 1e-10
+
+
+def test_time_varying_reference_with_the_nominal_model_is_the_constant_model_reference():
+    """The reference template compiled with `#define TIME_VARYING 1` (on-line block-Cholesky recursion, code_laxMPC_FISTA_C.c:139-262)
+    and called with the nominal A, B, Q, R, bounds reproduces the constant-model template: same k, u_opt to rounding.  This pins the
+    restated off-line ingredients (Alpha, Beta, QRi of spcies_b200/formulations/laxMPC.py) against the reference's own recursion."""
+    from spcies_b200 import sysmodel
+    ref, spec, cfg = _ref('TV_laxMPC_FISTA')
+    r0 = _ref('C2_laxMPC_FISTA')[0]
+    s = cfg['sys']
+    B = 64
+    b = sysmodel.synthetic_batch(s, B, seed=5)
+    tv = (np.tile(s['A'], (B, 1, 1)), np.tile(s['B'], (B, 1, 1)), np.tile(np.diag(cfg['param']['Q']), (B, 1)),
+          np.tile(np.diag(cfg['param']['R']), (B, 1)))
+    LB = np.tile(np.concatenate([s['LBx'], s['LBu']]), (B, 1))
+    UB = np.tile(np.concatenate([s['UBx'], s['UBu']]), (B, 1))
+    u, k, e = ref.solve_batch(b['x0'], b['xr'], b['ur'], tv=tv, LB=LB, UB=UB, threads=4)
+    u0, k0, e0 = r0.solve_batch(b['x0'], b['xr'], b['ur'])
+    assert np.array_equal(k, k0) and np.array_equal(e, e0)
+    assert np.max(np.abs(u - u0)) <= 1e-10

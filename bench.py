@@ -627,6 +627,36 @@ def main():
                   'how': 'single-instance symbol (batch of one: H2D, kernel, D2H): p50 of 200 calls from plain C (harness/main_batch) when '
                          'available, p50 / p99 of 1000 calls through ctypes; reference C solver: mean of %d identical solves, one thread' % nrep}
 
+    # ---- closed loop on the device: `steps` sampling times of u = MPC(x), x+ = A x + B u for every instance
+    closed = None
+    if cx.rank == 0 and cx.world == 1 and args.config == 'C2' and not args.no_others:
+        try:
+            from spcies_b200 import sysmodel as _sm
+            Bc, steps = 1 << 18, 20
+            bb = _sm.synthetic_batch(cfg['sys'], Bc, seed=400)
+            closed = {'instances': Bc, 'steps': steps, 'solver': spec.options.solver_key()}
+            for label, kw in (('cold', dict(warm_start=0)), ('warm_shifted', dict(warm_start=2)), ('warm_unshifted', dict(warm_start=1))):
+                sol.closed_loop(bb['x0'][:4096], bb['xr'][:4096], bb['ur'][:4096], 2, want_x=False, **kw)
+                t0 = time.perf_counter()
+                _, _, kk, ee, ci = sol.closed_loop(bb['x0'], bb['xr'], bb['ur'], steps, want_x=False, **kw)
+                dt = time.perf_counter() - t0
+                closed[label] = {'mpc_steps_per_s': Bc * steps / dt, 'seconds': dt, 'device_ms': ci['kernel_ms'], 'launches': ci['launches'],
+                                 'mean_k': ci['sum_k'] / (Bc * steps), 'n_not_converged': int(ci['n_not_converged'])}
+            # the round-1 way: one host-buffer batched call per sampling time, plant step on the host
+            AB = np.hstack([cfg['sys']['A'], cfg['sys']['B']])
+            x = bb['x0'].copy()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                uu = sol.solve_batch(x, bb['xr'], bb['ur'])[0]
+                x = x @ AB[:, :sol.n].T + uu @ AB[:, sol.n:].T
+            dt = time.perf_counter() - t0
+            closed['host_loop_of_batched_calls'] = {'mpc_steps_per_s': Bc * steps / dt, 'seconds': dt}
+            closed['how'] = ('<func>_closed_loop through the C ABI, host arrays in / trajectories out, wall clock; cold = every sampling time '
+                             'starts from lambda = 0 (a loop of reference calls), warm = from the dual point of the previous sampling time '
+                             '(unshifted: the `lambda` argument of spcies_laxMPC_FISTA_solver.m:161-164; shifted by one stage)')
+        except Exception as exn:                                     # pragma: no cover
+            closed = {'error': '%s: %s' % (type(exn).__name__, exn)}
+
     # ---- the other BASELINE configurations under the same contract, and configs[4] as stated (8 Mi instances, strong scaling)
     others, c5 = None, None
     if not args.no_others and args.config == 'C2':
@@ -660,7 +690,7 @@ def main():
             'dtype': 'f64', 'data': 'synthetic', 'config': head['config'], 'e2e': head['e2e'], 'gpu_launches': head['gpu_launches'],
             'clocks': clocks, 'roofline': head['roofline'], 'cpu_baseline': head['cpu_baseline'], 'parity': head['parity'],
             'single_solve': single, 'mean_k': head['mean_k'], 'n_not_converged_per_batch': head['n_not_converged_per_batch'],
-            'kernel': head['kernel'], 'other_configs': others, 'c5_sharded': c5, 'microbench': micro}
+            'kernel': head['kernel'], 'closed_loop': closed, 'other_configs': others, 'c5_sharded': c5, 'microbench': micro}
     print(json.dumps(line))
     if cx.world > 1:
         cx.dist.destroy_process_group()

@@ -10,7 +10,8 @@
  *
  * 1. single-instance call through the UNCHANGED reference symbol (same lines as main_cl_in_C.c:103), timing p50;
  * 2. batched call: B instances with random x0 around the closed-loop trajectory, solves/s;
- * 3. a batched closed loop: x+ = A x + B u for every instance between solves (main_cl_in_C.c:100-117).
+ * 3. the batched closed loop on the device: <func>_closed_loop (x+ = A x + B u for every instance between solves,
+ *    main_cl_in_C.c:100-117), cold and warm started.
  */
 #include SPCIES_HDR
 #include <math.h>
@@ -78,21 +79,42 @@ int main(int argc, char **argv) {
     printf("batch of %ld: %.2f ms end to end (%.2f ms kernel) = %.3g solves/s, mean k = %.1f, not converged = %ld\n", B, dt,
            info.kernel_ms, B / (dt * 1e-3), (double)info.sum_k / B, info.n_not_converged);
 
-    /* ---- 3. batched closed loop */
-    for (int t = 1; t <= steps; t++) {
-        rc = BATCH_FN(B, X, XR, UR, U, K, E, NULL, NULL, &info);
-        if (rc) return 1;
-        double xn[nn_], dist = 0.0;
-        for (long i = 0; i < B; i++) {
-            for (int r = 0; r < nn_; r++) {
-                xn[r] = 0.0;
-                for (int c = 0; c < nn_; c++) xn[r] += AB[r][c] * X[i * nn_ + c];
-                for (int c = 0; c < mm_; c++) xn[r] += AB[r][nn_ + c] * U[i * mm_ + c];
-            }
-            memcpy(&X[i * nn_], xn, sizeof xn);
-            for (int r = 0; r < 3; r++) dist += fabs(xn[r] - xr[r]);
+    /* ---- 3. batched closed loop ON THE DEVICE: <func>_closed_loop simulates `steps` sampling times of u_t = MPC(x_t),
+     *         x_{t+1} = A x_t + B u_t for every instance (main_cl_in_C.c:100-117) without a host round trip per sampling time;
+     *         the plant is the generated prediction model (opts.plant_AB = NULL) -- the AB fixture above is the same matrix */
+    if (steps > 0) {
+        double *XT = malloc(sizeof(double) * (steps + 1) * B * nn_), *UT = malloc(sizeof(double) * steps * B * mm_);
+        int *KT = malloc(sizeof(int) * steps * B), *ET = malloc(sizeof(int) * steps * B);
+        for (int warm = 0; warm <= 2; warm += 2) {
+            spcies_batch_opts o;
+            memset(&o, 0, sizeof o);
+            o.warm_start = warm;                       /* 0: cold start at every sampling time; 2: shifted dual point of the last one */
+            t0 = now_ms();
+            rc = CAT(SPCIES_FUNC, _closed_loop)(B, steps, X, XR, UR, XT, UT, KT, ET, &o, &info);
+            dt = now_ms() - t0;
+            if (rc) { fprintf(stderr, "closed loop failed: %s\n", spcies_cuda_last_error()); return 1; }
+            printf("closed loop (%s start), %d steps x %ld instances: %.2f ms (%.2f ms on the device, %ld launch(es)) = %.3g steps/s, mean k = %.1f\n",
+                   warm ? "shifted warm" : "cold", steps, B, dt, info.kernel_ms, info.launches, (double)steps * B / (dt * 1e-3),
+                   (double)info.sum_k / ((double)steps * B));
         }
-        printf("closed loop step %d: mean |x_pos - xr| = %.4f, mean k = %.1f\n", t, dist / (3.0 * B), (double)info.sum_k / B);
+        for (int t = 1; t <= steps; t++) {
+            double dist = 0.0, err = 0.0;
+            long kk = 0;
+            for (long i = 0; i < B; i++) {
+                const double *xp = XT + ((long)(t - 1) * B + i) * nn_, *xn = XT + ((long)t * B + i) * nn_, *uu = UT + ((long)(t - 1) * B + i) * mm_;
+                for (int r = 0; r < nn_; r++) {           /* the device's successor state against the fixture model */
+                    double a = 0.0;
+                    for (int c = 0; c < nn_; c++) a += AB[r][c] * xp[c];
+                    for (int c = 0; c < mm_; c++) a += AB[r][nn_ + c] * uu[c];
+                    if (fabs(a - xn[r]) > err) err = fabs(a - xn[r]);
+                }
+                for (int r = 0; r < 3; r++) dist += fabs(xn[r] - xr[r]);
+                kk += KT[(long)(t - 1) * B + i];
+            }
+            printf("closed loop step %d: mean |x_pos - xr| = %.4f, mean k = %.1f, max |x+ - AB (x; u)| = %.1e\n", t, dist / (3.0 * B),
+                   (double)kk / B, err);
+        }
+        free(XT); free(UT); free(KT); free(ET);
     }
     spcies_cuda_free();
     return 0;

@@ -51,9 +51,12 @@ template <class E> struct Plan {
     static constexpr int NPASS = (E::NO + NB - 1) / NB;
     static constexpr int STAGE_TILES = KI * NB;
     static constexpr size_t STAGE_BYTES = (size_t)STAGE_TILES * TILE_BYTES;
-    static constexpr int STAGES_PER_ITER = NPASS * NCH;
-    static constexpr size_t FRAG_BYTES = (size_t)STAGES_PER_ITER * STAGE_BYTES;
     static constexpr int TEAM = E::TEAM;
+    // the warps of a team take the passes round-robin; their stages interleave in the stream (round, chunk, rank) so that the
+    // ranks consume concurrently and a warp's next stage is always TEAM stages ahead (well inside the ring: no dead lock)
+    static constexpr int NROUND = (NPASS + TEAM - 1) / TEAM;
+    static constexpr int STAGES_PER_ITER = NROUND * NCH * TEAM;
+    static constexpr size_t FRAG_BYTES = (size_t)STAGES_PER_ITER * STAGE_BYTES;
     static constexpr int GROUP_TILES = E::NSTATE + NIN_PAD;          // iterates, then the input vector [w ; c ; padding]
     static constexpr size_t GROUP_BYTES = (size_t)GROUP_TILES * TILE_BYTES;
     static constexpr size_t SMALL_BYTES = (sizeof(typename E::Small) + 15) / 16 * 16;
@@ -124,17 +127,20 @@ static_assert(sizeof(Ctrl) <= 1536, "Ctrl");
 template <class E> static inline void fill_fragments(const long double *F, double2 *frag) {
     typedef Plan<E> P;
     constexpr int NINC = P::NIN * 8;
-    for (int pass = 0; pass < P::NPASS; ++pass)
+    for (int round = 0; round < P::NROUND; ++round)
         for (int ch = 0; ch < P::NCH; ++ch)
-            for (int ki = 0; ki < P::KI; ++ki)
-                for (int b = 0; b < P::NB; ++b)
-                    for (int lane = 0; lane < 32; ++lane) {
-                        const int ot = pass * P::NB + b, it = ch * P::KI + ki, o = lane / 4, t = lane % 4;
-                        double v[2] = {0.0, 0.0};
-                        if (ot < E::NO && it < P::NIN)
-                            for (int i = 0; i < 2; ++i) v[i] = (double)F[(size_t)(ot * 8 + o) * NINC + it * 8 + 2 * t + i];
-                        frag[((((size_t)pass * P::NCH + ch) * P::KI + ki) * P::NB + b) * 32 + lane] = make_double2(v[0], v[1]);
-                    }
+            for (int r = 0; r < P::TEAM; ++r)
+                for (int ki = 0; ki < P::KI; ++ki)
+                    for (int b = 0; b < P::NB; ++b)
+                        for (int lane = 0; lane < 32; ++lane) {
+                            const int pass = round * P::TEAM + r;           // passes beyond NPASS are zero padding
+                            const int ot = pass * P::NB + b, it = ch * P::KI + ki, o = lane / 4, t = lane % 4;
+                            double v[2] = {0.0, 0.0};
+                            if (pass < P::NPASS && ot < E::NO && it < P::NIN)
+                                for (int i = 0; i < 2; ++i) v[i] = (double)F[(size_t)(ot * 8 + o) * NINC + it * 8 + 2 * t + i];
+                            const size_t stage = ((size_t)round * P::NCH + ch) * P::TEAM + r;
+                            frag[((stage * P::KI + ki) * P::NB + b) * 32 + lane] = make_double2(v[0], v[1]);
+                        }
 }
 
 // ---- the kernel ----------------------------------------------------------------------------------------------------------------
@@ -272,7 +278,7 @@ template <class E> __global__ void __launch_bounds__(Plan<E>::BLOCK, 1) dense_mm
                 const int gsi = gs0 + idx, slot = P::RESIDENT ? idx : gsi % P::NSTAGE;
                 mbar_wait(&ctrl->full[slot], P::RESIDENT ? 0u : (unsigned)((gsi / P::NSTAGE) & 1));
                 const double2 *sp = reinterpret_cast<const double2 *>(ring + (size_t)slot * P::STAGE_BYTES) + lane;
-                const int it0 = (idx % P::NCH) * KI;
+                const int it0 = ((idx / TEAM) % P::NCH) * KI;
 #pragma unroll
                 for (int ki = 0; ki < KI; ++ki) {
                     v[ki] = win[(it0 + ki) * 32];
@@ -286,51 +292,50 @@ template <class E> __global__ void __launch_bounds__(Plan<E>::BLOCK, 1) dense_mm
                     if (lane == 0) mbar_arrive(&ctrl->empty[(gs0 + idx) % P::NSTAGE]);
                 }
             };
-            int pass = rank;
+            // this warp's stages: rank, rank + TEAM, rank + 2 TEAM, ...; NCH consecutive ones make a pass
             if (!__any_sync(FULL, live)) {
                 // nothing left in this warp: keep the stream in lock step (wait for a stage, hand it back), no loads, no MMAs
 #pragma unroll 1
-                for (; pass < P::NPASS; pass += TEAM)
-#pragma unroll 1
-                    for (int ch = 0; ch < P::NCH; ++ch) {
-                        const int idx = pass * P::NCH + ch, gsi = gs0 + idx, slot = P::RESIDENT ? idx : gsi % P::NSTAGE;
-                        mbar_wait(&ctrl->full[slot], P::RESIDENT ? 0u : (unsigned)((gsi / P::NSTAGE) & 1));
-                        release(idx);
-                    }
-            }
-            if (pass < P::NPASS) wait_load(pass * P::NCH, fc, vc);
-#pragma unroll 1
-            for (; pass < P::NPASS; pass += TEAM) {
-                double acc[NB][2];
-#pragma unroll
-                for (int b = 0; b < NB; ++b) acc[b][0] = acc[b][1] = 0.0;
-#pragma unroll 2
-                for (int ch = 0; ch < P::NCH; ++ch) {
-                    const int idx = pass * P::NCH + ch;
-                    // operands of the next stage of this warp are read while the MMAs of this one issue
-                    int nidx = idx + 1;
-                    if (ch == P::NCH - 1) nidx = (pass + TEAM) * P::NCH;
-                    double2 fn[KI][NB], vn[KI];
-                    const bool has_next = nidx < P::STAGES_PER_ITER;
-                    if (has_next) wait_load(nidx, fn, vn);
-#pragma unroll
-                    for (int ki = 0; ki < KI; ++ki) {
-#pragma unroll
-                        for (int b = 0; b < NB; ++b) dmma(acc[b][0], acc[b][1], vc[ki].x, fc[ki][b].x, acc[b][0], acc[b][1]);
-#pragma unroll
-                        for (int b = 0; b < NB; ++b) dmma(acc[b][0], acc[b][1], vc[ki].y, fc[ki][b].y, acc[b][0], acc[b][1]);
-                    }
+                for (int idx = rank; idx < P::STAGES_PER_ITER; idx += TEAM) {
+                    const int gsi = gs0 + idx, slot = P::RESIDENT ? idx : gsi % P::NSTAGE;
+                    mbar_wait(&ctrl->full[slot], P::RESIDENT ? 0u : (unsigned)((gsi / P::NSTAGE) & 1));
                     release(idx);
-                    if (has_next) {
+                }
+            } else {
+                wait_load(rank, fc, vc);
+#pragma unroll 1
+                for (int round = 0; round < P::NROUND; ++round) {
+                    double acc[NB][2];
+#pragma unroll
+                    for (int b = 0; b < NB; ++b) acc[b][0] = acc[b][1] = 0.0;
+#pragma unroll 2
+                    for (int ch = 0; ch < P::NCH; ++ch) {
+                        const int idx = (round * P::NCH + ch) * TEAM + rank;
+                        // operands of the next stage of this warp are read while the MMAs of this one issue
+                        const int nidx = idx + TEAM;
+                        double2 fn[KI][NB], vn[KI];
+                        const bool has_next = nidx < P::STAGES_PER_ITER;
+                        if (has_next) wait_load(nidx, fn, vn);
 #pragma unroll
                         for (int ki = 0; ki < KI; ++ki) {
-                            vc[ki] = vn[ki];
 #pragma unroll
-                            for (int b = 0; b < NB; ++b) fc[ki][b] = fn[ki][b];
+                            for (int b = 0; b < NB; ++b) dmma(acc[b][0], acc[b][1], vc[ki].x, fc[ki][b].x, acc[b][0], acc[b][1]);
+#pragma unroll
+                            for (int b = 0; b < NB; ++b) dmma(acc[b][0], acc[b][1], vc[ki].y, fc[ki][b].y, acc[b][0], acc[b][1]);
+                        }
+                        release(idx);
+                        if (has_next) {
+#pragma unroll
+                            for (int ki = 0; ki < KI; ++ki) {
+                                vc[ki] = vn[ki];
+#pragma unroll
+                                for (int b = 0; b < NB; ++b) fc[ki][b] = fn[ki][b];
+                            }
                         }
                     }
+                    const int pass = round * TEAM + rank;
+                    if (pass < P::NPASS) E::update(L, C, S, pass * NB, acc, st, t4, over);
                 }
-                E::update(L, C, S, pass * NB, acc, st, t4, over);
             }
         }
 

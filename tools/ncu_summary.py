@@ -14,7 +14,13 @@ KEYS = ['gpu__time_duration.sum', 'launch__registers_per_thread', 'launch__share
         'sm__cycles_elapsed.avg', 'smsp__average_warp_latency_per_inst_issued.ratio', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
         'smsp__inst_executed_op_shared_ld.sum', 'smsp__inst_executed_op_shared_st.sum', 'sm__inst_executed_pipe_fp64.sum',
         'sm__inst_executed_pipe_lsu.sum', 'l1tex__throughput.avg.pct_of_peak_sustained_elapsed',
-        'sm__throughput.avg.pct_of_peak_sustained_elapsed']
+        'sm__throughput.avg.pct_of_peak_sustained_elapsed',
+        # tensor pipe (DMMA.8x8x4 issues here): the counters that cross-check the fraction of the FP64 tensor ceiling
+        'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active', 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed',
+        'sm__inst_executed_pipe_tensor.sum', 'sm__inst_executed_pipe_tensor_op_dmma.sum',
+        'sm__pipe_tensor_op_dmma_cycles_active.avg.pct_of_peak_sustained_active',
+        'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed',
+        'sm__inst_executed_pipe_uniform.sum', 'lts__t_bytes.sum', 'lts__t_sector_hit_rate.pct']
 
 
 def main(path, grep=None):
@@ -28,6 +34,8 @@ def main(path, grep=None):
             if d.get(k) not in (None, ''):
                 print('   %-80s %s' % (k, d[k]))
         for k in hdr:
+            if 'tensor' in k and k not in KEYS and d.get(k) not in (None, '', '0', 'n/a'):     # every other tensor-pipe counter the report holds
+                print('   %-80s %s' % (k, d[k]))
             if grep and grep in k:
                 print('   %-80s %s' % (k, d[k]))
             if 'warps_issue_stalled' in k and k.endswith('.ratio') and 'not_issued' not in k:

@@ -157,6 +157,9 @@ template <class E> __global__ void __launch_bounds__(Plan<E>::BLOCK, 1) dense_mm
     const spcies_consts *C = reinterpret_cast<const spcies_consts *>(g_blob);
     const unsigned char *g_frag = g_blob + P::OFF_FRAG;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // every CTA starts the (circular) fragment stream at a different round: the order of the output passes within an iteration is
+    // free (every pass reads the same w), and 148 SMs walking one table in step would all hit the same L2 lines at the same time
+    const int r0 = P::RESIDENT ? 0 : (int)(blockIdx.x % P::NROUND);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < P::NSTAGE; ++s) mbar_init(&ctrl->full[s], 1);
@@ -181,7 +184,7 @@ template <class E> __global__ void __launch_bounds__(Plan<E>::BLOCK, 1) dense_mm
                 }
                 for (int s = 0; s < P::NSTAGE; ++s) mbar_wait(&ctrl->full[s], 0);     // never leave with copies in flight
             } else {
-                int issued = 0, slot = 0, idx = 0;     // idx: stage within the iteration
+                int issued = 0, slot = 0, idx = r0 * P::NCH * TEAM;     // idx: stage of the table (the stream starts at round r0)
                 unsigned par = 1;                      // parity of the `empty` phase to wait for (1: passes on a fresh barrier)
                 bool stopped = false;
                 for (;;) {
@@ -333,7 +336,7 @@ template <class E> __global__ void __launch_bounds__(Plan<E>::BLOCK, 1) dense_mm
                             }
                         }
                     }
-                    const int pass = round * TEAM + rank;
+                    const int pass = ((round + r0) % P::NROUND) * TEAM + rank;
                     if (pass < P::NPASS) E::update(L, C, S, pass * NB, acc, st, t4, over);
                 }
             }

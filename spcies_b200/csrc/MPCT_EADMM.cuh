@@ -297,6 +297,10 @@ struct Traits : PolicyTraits<Solver> {
         return arith != SPCIES_CUDA_ARITH_EXACT && io.sol == nullptr && io.engine != SPCIES_CUDA_ENGINE_SCALAR && io.LB == nullptr;
     }
     static bool uses_scratch(int arith, const BatchIO &io) { return !use_mma(arith, io); }
+    // the engine streams mu' (forward sweep -> backward sweep) through a per-warp global buffer
+    static size_t engine_scratch_bytes(int arith, const BatchIO &io, int grid) {
+        return use_mma(arith, io) ? (size_t)grid * MMA_WARPS * MUP_BYTES_PER_WARP : 0;
+    }
     static void engine_shape(int arith, const BatchIO &io, int &block, size_t &smem, int &ipb) {
         ipb = block;
         if (use_mma(arith, io)) {
@@ -312,7 +316,7 @@ struct Traits : PolicyTraits<Solver> {
             if (use_mma(arith, io)) {
                 cudaError_t e = cudaFuncSetAttribute(eadmm_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MMA_SMEM);
                 if (e != cudaSuccess) return e;
-                eadmm_mma_kernel<<<grid, MMA_BLOCK, MMA_SMEM, s>>>(io, (const unsigned char *)dc);
+                eadmm_mma_kernel<<<grid, MMA_BLOCK, MMA_SMEM, s>>>(io, (const unsigned char *)dc, (double2 *)scratch);
                 return cudaGetLastError();
             }
         }

@@ -7,10 +7,17 @@
 //   * z3_{l+1} = -H3i (q3 - [mu_l; 0] + [A B]' mu_{l+1})             2 MMA             (:291-320)
 //   * z2 = W2 q2                                                     2 MMA per iteration (:145-149)
 // With one thread per instance the 12.5 KB of iterates of an N = 50 instance (BASELINE.json configs[4]) only fit a global
-// scratch; here z1, z3, lambda and the forward-substituted mu' live in shared memory as [block][lane] double2 (4 N + 5 blocks,
-// 105 KB per warp at N = 50 -> two warps per SM), the per-stage component constants (rho, H1i, H3i) as one 64-byte row per
-// stage, and the recurrence fragments are streamed from global memory (L2) PF stages ahead when they do not fit beside the
-// iterates.
+// scratch.  Here z3 and lambda live in shared memory as [block][lane] double2 (2 N + 4 blocks = 53 KB per warp at N = 50 -> FOUR
+// warps per SM, one per scheduler; round 1 also kept z1 and mu' there: 105 KB per warp, two warps per SM, 2.9 % of the warp
+// slots -- the occupancy problem the round-1 profile showed):
+//   * z1 is not stored: z1_l = clip(H1i_l o (rho_l (z3_l + z2) + lambda_{l+1})) is recomputed from the *old* z3_l, lambda_{l+1}
+//     and z2 where the forward and the backward sweep need it (they still hold the old values at that point: a stage's z3 and
+//     lambda are overwritten at the end of its own backward step);
+//   * the forward-substituted mu' is a pure stream -- written stage by stage in the forward sweep, read in reverse in the
+//     backward sweep -- and goes to a per-warp global scratch (L2 resident: 25 KB per warp), read back PF stages ahead through a
+//     register ring like the recurrence fragments;
+//   * the per-stage component constants (rho, H1i, H3i) are one 64-byte row per stage, the recurrence fragments are streamed from
+//     global memory (L2) PF stages ahead.
 //
 // Arithmetic: FAST (FMA, explicit block inverses, dot products in the MMA's order, q2 accumulated in two interleaved partial
 // sums; [T xr; S ur] computed once per instance).  EXACT mode, float and the debug payload use the scalar kernel.
@@ -23,8 +30,8 @@
 
 constexpr bool MMA_SHAPE_OK = n >= 5 && n <= 6 && nm <= 8 && N >= 3;
 constexpr int PF = 4;                                             // prefetch distance (stages) of the recurrence fragments
-constexpr int MMA_NBLK = 4 * N + 5;                               // z1[N+1], z3[N+1], lambda[N+3], mu'[N]
-constexpr int BLK_Z1 = 0, BLK_Z3 = N + 1, BLK_LAM = 2 * N + 2, BLK_MUP = 3 * N + 5;
+constexpr int MMA_NBLK = 2 * N + 4;                               // z3[N+1], lambda[N+3]   (z1 recomputed, mu' streamed through L2)
+constexpr int BLK_Z3 = 0, BLK_LAM = N + 1;
 constexpr size_t MMA_STATE_PER_WARP = (size_t)MMA_NBLK * 32 * sizeof(double2);
 
 struct alignas(16) MmaSmall {   // staged into shared memory
@@ -43,10 +50,12 @@ constexpr size_t CONSTS_BYTES_ = (sizeof(spcies_consts) + 15) / 16 * 16;
 constexpr size_t MMA_OFFSET = CONSTS_BYTES_;                      // blob: spcies_consts | MmaSmall | MmaFrag
 constexpr size_t SMEM_LIMIT = 227 * 1024 - 64;
 constexpr int warps_fit(size_t fixed) { return fixed >= SMEM_LIMIT ? 0 : (int)((SMEM_LIMIT - fixed) / MMA_STATE_PER_WARP); }
-// fragments in shared memory if that still leaves room for at least two warps; else streamed from global memory
-constexpr bool FRAG_SMEM = warps_fit(SMALL_BYTES + FRAG_BYTES) >= 2;
+// fragments in shared memory only if that does not cost a warp (up to one warp per SM scheduler); else streamed from global memory
+constexpr int cap4(int w) { return w > 4 ? 4 : w; }
+constexpr bool FRAG_SMEM = cap4(warps_fit(SMALL_BYTES + FRAG_BYTES)) >= cap4(warps_fit(SMALL_BYTES));
 constexpr int MMA_WARPS_RAW = warps_fit(SMALL_BYTES + (FRAG_SMEM ? FRAG_BYTES : 0));
 constexpr int MMA_WARPS = MMA_WARPS_RAW > 8 ? 8 : MMA_WARPS_RAW;
+constexpr size_t MUP_BYTES_PER_WARP = (size_t)N * 32 * sizeof(double2);   // the mu' stream of a warp (global scratch)
 constexpr int MMA_BLOCK = MMA_WARPS * 32;
 constexpr int MMA_IPB = MMA_WARPS * 8;
 constexpr size_t MMA_STAGED = SMALL_BYTES + (FRAG_SMEM ? FRAG_BYTES : 0);
@@ -96,7 +105,8 @@ static inline void fill_mma_tables(const spcies_consts &C, MmaSmall &S, MmaFrag 
     delete[] Linv;
 }
 
-__global__ void __launch_bounds__(MMA_BLOCK, 1) eadmm_mma_kernel(const BatchIO io, const unsigned char *__restrict__ g_blob) {
+__global__ void __launch_bounds__(MMA_BLOCK, 1) eadmm_mma_kernel(const BatchIO io, const unsigned char *__restrict__ g_blob,
+                                                                 double2 *__restrict__ g_mup) {
     using mma::dmma;
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -115,6 +125,7 @@ __global__ void __launch_bounds__(MMA_BLOCK, 1) eadmm_mma_kernel(const BatchIO i
     const unsigned gmask = 0xFu << (4 * g);
     const bool leader = t4 == 0, lo2 = t4 < 2;
     double2 *st = reinterpret_cast<double2 *>(smem_raw + MMA_STAGED + warp * MMA_STATE_PER_WARP) + lane;
+    double2 *gm = g_mup + ((size_t)blockIdx.x * MMA_WARPS + warp) * (size_t)(N * 32) + lane;    // mu'_l of this lane at gm[l * 32]
     auto LD = [&](int blk) { return st[blk * 32]; };
     auto ST = [&](int blk, double2 v) { st[blk * 32] = v; };
     auto ROW = [&](const double (*tab)[8], int l) { return reinterpret_cast<const double2 *>(tab[l])[t4]; };   // (tab[l][2t], tab[l][2t+1])
@@ -179,6 +190,21 @@ __global__ void __launch_bounds__(MMA_BLOCK, 1) eadmm_mma_kernel(const BatchIO i
         }
         if (!__any_sync(FULL, live)) break;
         bool over = false;
+        const double z2o[2] = {z2[0], z2[1]};       // z2 of the previous iteration: what every z1 of this iteration is computed from
+        const double2 lam0o = LD(BLK_LAM + 0);      // lambda_0 of the previous iteration (enters z1_0)
+        // z1_l, l < N, from the old z3_l / lambda_{l+1} / z2                                 :97-110
+        auto z1_of = [&](int l, const double2 z3l, const double2 l1) {
+            const double2 rl = ROW(T->rho, l), h1 = ROW(T->H1i, l);
+            double2 v;
+            if (l == 0) {
+                v.x = clip((fma(rho0.x, x0v[0], rl.x * (z3l.x + z2o[0])) + l1.x - lam0o.x) * h1.x, lb0.x, ub0.x);
+                v.y = clip((fma(rho0.y, x0v[1], rl.y * (z3l.y + z2o[1])) + l1.y - lam0o.y) * h1.y, lb0.y, ub0.y);
+            } else {
+                v.x = clip(fma(rl.x, z3l.x + z2o[0], l1.x) * h1.x, lbi.x, ubi.x);
+                v.y = clip(fma(rl.y, z3l.y + z2o[1], l1.y) * h1.y, lbi.y, ubi.y);
+            }
+            return v;
+        };
 
         // ---------- P1, last block first, and the head of q2                              :112-117, :123-136
         double q2a[2], q2b[2] = {0.0, 0.0}, z1N[2];
@@ -194,23 +220,13 @@ __global__ void __launch_bounds__(MMA_BLOCK, 1) eadmm_mma_kernel(const BatchIO i
                 z1N[i] = v;
                 q2a[i] = fma(-rs, v, rz) + la[i] + lb_[i] + tq[i];
             }
-            ST(BLK_Z1 + N, make_double2(z1N[0], z1N[1]));
         }
         // ---------- P1 for l = 0..N-1 fused with the q2 accumulation                      :97-110, :137-141
         {
-            const double2 lam0 = LD(BLK_LAM + 0);
 #pragma unroll 2
             for (int l = 0; l < N; ++l) {
-                const double2 z3l = LD(BLK_Z3 + l), l1 = LD(BLK_LAM + l + 1), rl = ROW(T->rho, l), h1 = ROW(T->H1i, l);
-                double2 v;
-                if (l == 0) {
-                    v.x = clip((fma(rho0.x, x0v[0], rl.x * (z3l.x + z2[0])) + l1.x - lam0.x) * h1.x, lb0.x, ub0.x);
-                    v.y = clip((fma(rho0.y, x0v[1], rl.y * (z3l.y + z2[1])) + l1.y - lam0.y) * h1.y, lb0.y, ub0.y);
-                } else {
-                    v.x = clip(fma(rl.x, z3l.x + z2[0], l1.x) * h1.x, lbi.x, ubi.x);
-                    v.y = clip(fma(rl.y, z3l.y + z2[1], l1.y) * h1.y, lbi.y, ubi.y);
-                }
-                ST(BLK_Z1 + l, v);
+                const double2 z3l = LD(BLK_Z3 + l), l1 = LD(BLK_LAM + l + 1), rl = ROW(T->rho, l);
+                const double2 v = z1_of(l, z3l, l1);
                 if (l & 1) {
                     q2b[0] += fma(rl.x, z3l.x - v.x, l1.x);
                     q2b[1] += fma(rl.y, z3l.y - v.y, l1.y);
@@ -231,7 +247,8 @@ __global__ void __launch_bounds__(MMA_BLOCK, 1) eadmm_mma_kernel(const BatchIO i
         }
         // ---------- P3 forward: t_l = H3i_l o q3_l,  rhs_l = t_{l+1} - [A B] t_l,  mu'_l   :157-184, :221-251
         auto t_of = [&](int l, double (&t)[2]) {     // q3_l = lambda_{l+1} + rho_l (z2 - z1_l)
-            const double2 la = LD(BLK_LAM + l + 1), z1 = LD(BLK_Z1 + l), rl = ROW(T->rho, l), h3 = ROW(T->H3i, l);
+            const double2 la = LD(BLK_LAM + l + 1), rl = ROW(T->rho, l), h3 = ROW(T->H3i, l);
+            const double2 z1 = l == N ? make_double2(z1N[0], z1N[1]) : z1_of(l, LD(BLK_Z3 + l), la);
             t[0] = h3.x * fma(rl.x, z2[0] - z1.x, la.x);
             t[1] = h3.y * fma(rl.y, z2[1] - z1.y, la.y);
         };
@@ -259,7 +276,7 @@ __global__ void __launch_bounds__(MMA_BLOCK, 1) eadmm_mma_kernel(const BatchIO i
                         dmma(e0, e1, r[0], fa[j].x, 0.0, 0.0);
                         dmma(f0, f1, mup[0], fa[j].y, e0, e1);               // F_0 = 0
                         dmma(mup[0], mup[1], lo2 ? r[1] : mup[1], fb[j], f0, f1);
-                        ST(BLK_MUP + l, make_double2(mup[0], mup[1]));
+                        gm[l * 32] = make_double2(mup[0], mup[1]);          // mu'_l: streamed out, read back by the backward sweep
                         ta[0] = tb[0];
                         ta[1] = tb[1];
                         const int ln = l + PF < N ? l + PF : N - 1;
@@ -269,24 +286,31 @@ __global__ void __launch_bounds__(MMA_BLOCK, 1) eadmm_mma_kernel(const BatchIO i
                 }
             }
         }
+        double2 z10 = make_double2(0.0, 0.0);     // z1_0 of this iteration (u_opt, res_0): recomputed in the last backward stage
         // ---------- P3 backward + z3 + residual + lambda + exit tests                      :254-320, :371-449
         // close_stage: res = z2 + z3_l - z1_l, lambda_{l+1} += rho_l res, |res|, |z3_prev - z3| tests
-        auto close_stage = [&](int l, const double (&z3n)[2]) {
-            const double2 z1 = LD(BLK_Z1 + l), z3o = LD(BLK_Z3 + l), la = LD(BLK_LAM + l + 1), rl = ROW(T->rho, l);
+        auto close_stage = [&](int l, const double (&z3n)[2], const double2 z1, const double2 z3o, const double2 la) {
+            const double2 rl = ROW(T->rho, l);
             const double r0 = (z2[0] + z3n[0]) - z1.x, r1 = (z2[1] + z3n[1]) - z1.y;
             over = over || (fabs(r0) > tolz[0]) || (fabs(r1) > tolz[1]) || (fabs(z3o.x - z3n[0]) > tolz[0]) || (fabs(z3o.y - z3n[1]) > tolz[1]);
             ST(BLK_Z3 + l, make_double2(z3n[0], z3n[1]));
             ST(BLK_LAM + l + 1, make_double2(fma(rl.x, r0, la.x), fma(rl.y, r1, la.y)));
         };
-        auto q3_of = [&](int l, double (&q)[2]) {
-            const double2 la = LD(BLK_LAM + l + 1), z1 = LD(BLK_Z1 + l), rl = ROW(T->rho, l);
+        auto q3_of = [&](int l, double (&q)[2], const double2 z1, const double2 la) {
+            const double2 rl = ROW(T->rho, l);
             q[0] = fma(rl.x, z2[0] - z1.x, la.x);
             q[1] = fma(rl.y, z2[1] - z1.y, la.y);
+        };
+        // old z3_l, lambda_{l+1} and the z1_l they give: read once per stage of the backward sweep, before they are overwritten
+        auto stage_in = [&](int l, double2 &z1, double2 &z3o, double2 &la) {
+            z3o = LD(BLK_Z3 + l);
+            la = LD(BLK_LAM + l + 1);
+            z1 = l == N ? make_double2(z1N[0], z1N[1]) : z1_of(l, z3o, la);
         };
         {
             double mu[2], mun[2];     // mu_{l+1}, mu_l
             {
-                const double2 mp = LD(BLK_MUP + N - 1), ba = BWA(N - 1);
+                const double2 mp = gm[(N - 1) * 32], ba = BWA(N - 1);
                 const double bb = BWB(N - 1);
                 double g0, g1;
                 dmma(g0, g1, mp.x, ba.x, 0.0, 0.0);
@@ -294,18 +318,21 @@ __global__ void __launch_bounds__(MMA_BLOCK, 1) eadmm_mma_kernel(const BatchIO i
             }
             {   // z3_N = -H3i_N o (q3_N - [mu_{N-1}; 0])
                 double q[2], z3n[2];
-                q3_of(N, q);
+                double2 z1, z3o, la;
+                stage_in(N, z1, z3o, la);
+                q3_of(N, q, z1, la);
                 const double2 h3 = ROW(T->H3i, N);
                 z3n[0] = -h3.x * fma(-maskx[0], mu[0], q[0]);
                 z3n[1] = -h3.y * fma(-maskx[1], mu[1], q[1]);
-                close_stage(N, z3n);
+                close_stage(N, z3n, z1, z3o, la);
             }
-            double2 ba[PF];
+            double2 ba[PF], mpr[PF];
             double bb[PF];
 #pragma unroll
             for (int j = 0; j < PF; ++j) {
                 ba[j] = BWA(N - 2 - j >= 0 ? N - 2 - j : 0);
                 bb[j] = BWB(N - 2 - j >= 0 ? N - 2 - j : 0);
+                mpr[j] = gm[(N - 2 - j >= 0 ? N - 2 - j : 0) * 32];
             }
 #pragma unroll 1
             for (int l0 = N - 2; l0 >= 0; l0 -= PF) {
@@ -313,42 +340,46 @@ __global__ void __launch_bounds__(MMA_BLOCK, 1) eadmm_mma_kernel(const BatchIO i
                 for (int j = 0; j < PF; ++j) {
                     const int l = l0 - j;
                     if (l >= 0) {
-                        const double2 mp = LD(BLK_MUP + l);
+                        const double2 mp = mpr[j];
                         double g0, g1, h0, h1;
                         dmma(g0, g1, mp.x, ba[j].x, 0.0, 0.0);
                         dmma(h0, h1, mu[0], ba[j].y, g0, g1);
                         dmma(mun[0], mun[1], lo2 ? mp.y : mu[1], bb[j], h0, h1);
                         // z3_{l+1} = -H3i_{l+1} o (q3_{l+1} - [mu_l; 0] + [A B]' mu_{l+1})
                         double q[2], a[2], z3n[2];
-                        q3_of(l + 1, q);
+                        double2 z1, z3o, la;
+                        stage_in(l + 1, z1, z3o, la);
+                        q3_of(l + 1, q, z1, la);
                         mma::mv(a, abt, mu, fma(-maskx[0], mun[0], q[0]), fma(-maskx[1], mun[1], q[1]));
                         const double2 h3 = ROW(T->H3i, l + 1);
                         z3n[0] = -h3.x * a[0];
                         z3n[1] = -h3.y * a[1];
-                        close_stage(l + 1, z3n);
+                        close_stage(l + 1, z3n, z1, z3o, la);
                         mu[0] = mun[0];
                         mu[1] = mun[1];
                         const int ln = l - PF >= 0 ? l - PF : 0;
                         ba[j] = BWA(ln);
                         bb[j] = BWB(ln);
+                        mpr[j] = gm[ln * 32];
                     }
                 }
             }
             {   // z3_0 = -H3i_0 o (q3_0 + [A B]' mu_0)
                 double q[2], a[2], z3n[2];
-                q3_of(0, q);
+                double2 z1, z3o, la;
+                stage_in(0, z1, z3o, la);
+                z10 = z1;
+                q3_of(0, q, z1, la);
                 mma::mv(a, abt, mu, q[0], q[1]);
                 const double2 h3 = ROW(T->H3i, 0);
                 z3n[0] = -h3.x * a[0];
                 z3n[1] = -h3.y * a[1];
-                close_stage(0, z3n);
+                close_stage(0, z3n, z1, z3o, la);
             }
         }
         // res_0 = z1_0[0:n] - x0, lambda_0;  res_{N+2} = z2 - z1_N, lambda_{N+2}             :371-402
-        double2 z10;
         {
-            z10 = LD(BLK_Z1 + 0);
-            const double2 l0 = LD(BLK_LAM + 0), lS = LD(BLK_LAM + N + 2);
+            const double2 l0 = lam0o, lS = LD(BLK_LAM + N + 2);
             const double r0 = z10.x - x0v[0], r1 = z10.y - x0v[1];
             const double s0 = z2[0] - z1N[0], s1 = z2[1] - z1N[1];
             over = over || (fabs(r0) > tolx[0]) || (fabs(r1) > tolx[1]) || (fabs(s0) > tolz[0]) || (fabs(s1) > tolz[1]);

@@ -789,6 +789,7 @@ struct Traits {
     }
     static size_t scratch_bytes(int, int, bool) { return 0; }
     static bool uses_scratch(int, const BatchIO &) { return false; }
+    static size_t engine_scratch_bytes(int, const BatchIO &, int) { return 0; }
     static cudaError_t launch(int arith, bool varb, int grid, int block, size_t smem, cudaStream_t s, const BatchIO &io,
                               const void *dc, void *) {
         const bool ex = arith == SPCIES_CUDA_ARITH_EXACT;

@@ -288,7 +288,8 @@ template <class Traits> struct Runtime {
         int grid = (int)((B + ipb - 1) / ipb);
         if (cl.grid > 0 && cl.grid < grid) grid = cl.grid;
         if (grid > c.sm_count) grid = c.sm_count;
-        const size_t need_scratch = Traits::uses_scratch(cl.arith, io) ? Traits::scratch_bytes(grid, block, varb) : 0;
+        const size_t need_scratch = std::max<size_t>(Traits::uses_scratch(cl.arith, io) ? Traits::scratch_bytes(grid, block, varb) : 0,
+                                                     Traits::engine_scratch_bytes(cl.arith, io, grid));
         if (need_scratch > c.cap_scratch) {
             c.cap_scratch = 0;
             if (c.d_scratch) SPCIES_CK(cudaFree(c.d_scratch));
@@ -368,7 +369,8 @@ template <class Traits> struct Runtime {
         long long want = (B + ipb - 1) / ipb;
         int grid = cl.grid > 0 ? cl.grid : c.sm_count;   // persistent: one CTA per SM
         if (want < grid) grid = (int)(want > 0 ? want : 1);
-        const size_t need_scratch = Traits::uses_scratch(cl.arith, io) ? Traits::scratch_bytes(grid, block, varb) : 0;
+        const size_t need_scratch = std::max<size_t>(Traits::uses_scratch(cl.arith, io) ? Traits::scratch_bytes(grid, block, varb) : 0,
+                                                     Traits::engine_scratch_bytes(cl.arith, io, grid));
         if (need_scratch > c.cap_scratch) {
             c.cap_scratch = 0;
             if (c.d_scratch) SPCIES_CK(cudaFree(c.d_scratch));
@@ -567,7 +569,8 @@ template <class Traits> struct Runtime {
         long long want = (B + ipb - 1) / ipb;
         int grid = c.sm_count;
         if (want < grid) grid = (int)(want > 0 ? want : 1);
-        const size_t need_scratch = Traits::uses_scratch(cl.arith, io) ? Traits::scratch_bytes(grid, block, false) : 0;
+        const size_t need_scratch = std::max<size_t>(Traits::uses_scratch(cl.arith, io) ? Traits::scratch_bytes(grid, block, false) : 0,
+                                                     Traits::engine_scratch_bytes(cl.arith, io, grid));
         if (need_scratch > c.cap_scratch) {
             c.cap_scratch = 0;
             if (c.d_scratch) SPCIES_CK(cudaFree(c.d_scratch));

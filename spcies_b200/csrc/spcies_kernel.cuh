@@ -144,6 +144,7 @@ template <class S> struct PolicyTraits {
     static bool caps_engine(int, const BatchIO &) { return false; }
     static bool cl_engine(int, const BatchIO &) { return false; }     // no in-kernel closed loop: one launch per sampling time
     static bool uses_scratch(int, const BatchIO &) { return true; }   // the global per-instance state of the scalar kernels
+    static size_t engine_scratch_bytes(int, const BatchIO &, int) { return 0; }   // global scratch of a tensor-core engine, if any
     static constexpr int K_MAX = 0;
     static cudaError_t init_device_symbols() { return cudaSuccess; }
     static int default_block(bool varb) { return varb ? P::BLOCK_VARB : P::BLOCK_FIXED; }

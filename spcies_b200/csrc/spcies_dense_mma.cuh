@@ -46,7 +46,7 @@ template <class E> struct Plan {
     static constexpr int NB = E::NB;
     static constexpr int KI = 2;                                     // input tiles per stage
     static constexpr int NIN = E::NW + E::NC;
-    static constexpr int NCH = (NIN + KI - 1) / KI;                  // chunks (stages) per pass
+    static constexpr int NCH = (NIN + 2 * KI - 1) / (2 * KI) * 2;    // chunks (stages) per pass: even, the consumer loop handles them in pairs
     static constexpr int NIN_PAD = NCH * KI;
     static constexpr int NPASS = (E::NO + NB - 1) / NB;
     static constexpr int STAGE_TILES = KI * NB;
@@ -277,11 +277,11 @@ template <class E> __global__ void __launch_bounds__(Plan<E>::BLOCK, 1) dense_mm
         {
             const int gs0 = iter * P::STAGES_PER_ITER;       // global index of this iteration's first stage
             double2 fc[KI][NB], vc[KI];
-            auto wait_load = [&](int idx, double2 (&f)[KI][NB], double2 (&v)[KI]) {
+            auto wait_load = [&](int idx, int ch, double2 (&f)[KI][NB], double2 (&v)[KI]) {   // ch: the chunk of its pass (input tiles ch KI ..)
                 const int gsi = gs0 + idx, slot = P::RESIDENT ? idx : gsi % P::NSTAGE;
                 mbar_wait(&ctrl->full[slot], P::RESIDENT ? 0u : (unsigned)((gsi / P::NSTAGE) & 1));
                 const double2 *sp = reinterpret_cast<const double2 *>(ring + (size_t)slot * P::STAGE_BYTES) + lane;
-                const int it0 = ((idx / TEAM) % P::NCH) * KI;
+                const int it0 = ch * KI;
 #pragma unroll
                 for (int ki = 0; ki < KI; ++ki) {
                     v[ki] = win[(it0 + ki) * 32];
@@ -305,36 +305,35 @@ template <class E> __global__ void __launch_bounds__(Plan<E>::BLOCK, 1) dense_mm
                     release(idx);
                 }
             } else {
-                wait_load(rank, fc, vc);
+                // Two operand buffers, stages taken in pairs: the operands of the next stage are read from shared memory while the
+                // MMAs of the current one issue, and the hand-over is a renaming (no register moves, no predicates).  The chunk
+                // loop is fully unrolled, so the input tiles are read at constant offsets.
+                double2 fb[KI][NB], vb[KI];
+                auto mmas = [&](double (&acc)[NB][2], const double2 (&f)[KI][NB], const double2 (&v)[KI]) {
+#pragma unroll
+                    for (int ki = 0; ki < KI; ++ki) {
+#pragma unroll
+                        for (int b = 0; b < NB; ++b) dmma(acc[b][0], acc[b][1], v[ki].x, f[ki][b].x, acc[b][0], acc[b][1]);
+#pragma unroll
+                        for (int b = 0; b < NB; ++b) dmma(acc[b][0], acc[b][1], v[ki].y, f[ki][b].y, acc[b][0], acc[b][1]);
+                    }
+                };
+                wait_load(rank, 0, fc, vc);
 #pragma unroll 1
                 for (int round = 0; round < P::NROUND; ++round) {
                     double acc[NB][2];
 #pragma unroll
                     for (int b = 0; b < NB; ++b) acc[b][0] = acc[b][1] = 0.0;
-#pragma unroll 2
-                    for (int ch = 0; ch < P::NCH; ++ch) {
-                        const int idx = (round * P::NCH + ch) * TEAM + rank;
-                        // operands of the next stage of this warp are read while the MMAs of this one issue
-                        const int nidx = idx + TEAM;
-                        double2 fn[KI][NB], vn[KI];
-                        const bool has_next = nidx < P::STAGES_PER_ITER;
-                        if (has_next) wait_load(nidx, fn, vn);
+                    const int base = round * P::NCH * TEAM + rank;
 #pragma unroll
-                        for (int ki = 0; ki < KI; ++ki) {
-#pragma unroll
-                            for (int b = 0; b < NB; ++b) dmma(acc[b][0], acc[b][1], vc[ki].x, fc[ki][b].x, acc[b][0], acc[b][1]);
-#pragma unroll
-                            for (int b = 0; b < NB; ++b) dmma(acc[b][0], acc[b][1], vc[ki].y, fc[ki][b].y, acc[b][0], acc[b][1]);
-                        }
+                    for (int ch = 0; ch < P::NCH; ch += 2) {
+                        const int idx = base + ch * TEAM;
+                        wait_load(idx + TEAM, ch + 1, fb, vb);                  // stage ch + 1 of this pass
+                        mmas(acc, fc, vc);
                         release(idx);
-                        if (has_next) {
-#pragma unroll
-                            for (int ki = 0; ki < KI; ++ki) {
-                                vc[ki] = vn[ki];
-#pragma unroll
-                                for (int b = 0; b < NB; ++b) fc[ki][b] = fn[ki][b];
-                            }
-                        }
+                        if (ch + 2 < P::NCH || round + 1 < P::NROUND) wait_load(idx + 2 * TEAM, (ch + 2) % P::NCH, fc, vc);   // the stage after it
+                        mmas(acc, fb, vb);
+                        release(idx + TEAM);
                     }
                     const int pass = ((round + r0) % P::NROUND) * TEAM + rank;
                     if (pass < P::NPASS) E::update(L, C, S, pass * NB, acc, st, t4, over);

@@ -34,7 +34,7 @@ def main(path, grep=None):
             if d.get(k) not in (None, ''):
                 print('   %-80s %s' % (k, d[k]))
         for k in hdr:
-            if 'tensor' in k and k not in KEYS and d.get(k) not in (None, '', '0', 'n/a'):     # every other tensor-pipe counter the report holds
+            if 'tensor' in k and 'ops_path' not in k and 'attribute' not in k and k not in KEYS and d.get(k) not in (None, '', '0', 'n/a'):     # every other tensor-pipe counter the report holds
                 print('   %-80s %s' % (k, d[k]))
             if grep and grep in k:
                 print('   %-80s %s' % (k, d[k]))

@@ -47,14 +47,17 @@ WORKLOADS = {
     'C4': ('C4_ellipMPC_ADMM_soc', 1 << 20, 1 << 14, 'ellipMPC ADMM_soc (proj_SOC terminal constraint) N=10, 1Mi-instance batch per GPU'),
     'C5a': ('C5a_HMPC_SADMM_split', 1 << 17, 512, 'HMPC SADMM_split N=50, 128Ki-instance shard per GPU'),
     'C5b': ('C5b_MPCT_EADMM', 1 << 20, 1 << 14, 'MPCT EADMM N=50, 1Mi-instance shard per GPU'),
-    'C3f': ('C3f_equMPC_ADMM', 1 << 20, 1 << 14, 'equMPC ADMM oscillating masses N=20, 1Mi-instance batch per GPU, precision = float'),
+    'C3f': ('C3f_equMPC_ADMM', 1 << 20, 1 << 14, 'equMPC ADMM oscillating masses N=20, 1Mi-instance batch per GPU, precision = float '
+                                                 '(float constants, double arithmetic: what the reference float solver computes)'),
+    'C3ff': ('C3ff_equMPC_ADMM', 1 << 20, 1 << 14, 'equMPC ADMM oscillating masses N=20, 1Mi-instance batch per GPU, precision = float with '
+                                                   'true single-precision arithmetic (float_arithmetic)'),
     # solvers added in round 2, at the reference tests' problem (N = 10) with the default tolerances
     'C6': ('C6_MPCT_ADMM_cs', 1 << 18, 1 << 12, 'MPCT ADMM_cs (extended state space) N=10, 256Ki-instance batch per GPU'),
     'C7': ('C7_HMPC_ADMM', 1 << 18, 1 << 12, 'HMPC ADMM (non-split, the toolbox default for HMPC) N=10, 256Ki-instance batch per GPU'),
     'C8': ('C8_MPCT_ADMM_semiband', 1 << 18, 1 << 12, 'MPCT ADMM_semiband (banded + low-rank QP step) N=10, 256Ki-instance batch per GPU'),
 }
 # configurations measured next to the headline in the default run (2 timed steps each): `other_configs` of the JSON line
-OTHER_CONFIGS = ('C3', 'C3f', 'C4', 'C5a', 'C5b', 'C6', 'C7', 'C8')
+OTHER_CONFIGS = ('C3', 'C3f', 'C3ff', 'C4', 'C5a', 'C5b', 'C6', 'C7', 'C8')
 KERNELS = {'laxMPC_FISTA': 'spcies::fista::fista_mma_kernel', 'equMPC_ADMM': 'spcies::admm::admm_mma_kernel',
            'ellipMPC_ADMM_soc': 'spcies::soc::soc_mma_kernel', 'MPCT_EADMM': 'spcies::eadmm::eadmm_mma_kernel',
            'HMPC_SADMM_split': 'spcies::dense::dense_mma_kernel<hmpc::Engine>', 'HMPC_ADMM_split': 'spcies::dense::dense_mma_kernel<hmpc::Engine>',
@@ -369,7 +372,7 @@ def measure(cx, config_name, W, K, micro, peaks, peak_kind, batch=0, seeds_base=
         cores = os.cpu_count() or 1
         rate_all, dt_all, _, _, _ = cpu_reference_leg(save_name, b0, sample, cores)
         u, k, e = h_u.numpy()[:sample], h_k.numpy()[:sample], h_e.numpy()[:sample]
-        parity = parity_block(spec, u, k, e, ur_, kr, er, 1e-5 if sol.precision == 'float' else 1e-9)
+        parity = parity_block(spec, u, k, e, ur_, kr, er, 1e-5 if sol.arithmetic == 'float' else 1e-9)
         cpu_baseline = {'value': rate1, 'unit': 'solves/s', 'cores': 1, 'kind': 'reference',
                         'sample': f'first {sample} instances of the last timed batch; instantiated reference template, '
                                   f'gcc -O3, DEBUG/MEASURE_TIME off; {dt1:.1f} s',
@@ -379,7 +382,7 @@ def measure(cx, config_name, W, K, micro, peaks, peak_kind, batch=0, seeds_base=
     sum_k_all = cx.sum_over_ranks(sum_k)
     fma = fma_per_instance(spec.options.solver_key(), dims, sum_k, B, spec)
     achieved_tflops = 2.0 * fma / (kernel_ms * 1e-3) / 1e12
-    is_float = sol.precision == 'float'
+    is_float = sol.arithmetic == 'float'
     if micro and 'fp64_tfma_per_s' in micro:
         fp_peak = 2.0 * (micro.get('fp32_tfma_per_s', 0.0) if is_float else
                          max(micro.get('fp64_tfma_per_s', 0.0), micro.get('fp64_dmma_tfma_per_s', 0.0)))
@@ -404,6 +407,7 @@ def measure(cx, config_name, W, K, micro, peaks, peak_kind, batch=0, seeds_base=
     out = {'value': value, 'unit': 'solves/s', 'steps': K, 'warmup': W, 'ms_per_step': t_dev_ms / K,
            'config': {'workload': desc, 'solver': spec.options.solver_key(), 'N': dims['N'], 'batch_per_gpu': B,
                       'tol': spec.define('tol', spec.define('tol_p')), 'k_max': spec.define('k_max'), 'precision': sol.precision,
+                      'arithmetic': sol.arithmetic,
                       'l2': ('L2 flushed (256 MiB write) before every timed step' if flush else
                              'inputs larger than L2: %d distinct batches rotated between steps' % nb)},
            'dtype': 'f32' if is_float else 'f64',

@@ -121,7 +121,9 @@ typedef struct {
 int         spcies_cuda_abi_version(void);
 const char *spcies_cuda_solver_name(void);     /* "<F>_<method>[_<sub>]", e.g. "laxMPC_FISTA"            */
 const char *spcies_cuda_save_name(void);       /* the save_name the solver was generated with             */
-const char *spcies_cuda_precision(void);       /* "double" | "float": arithmetic type of the kernels      */
+const char *spcies_cuda_precision(void);       /* "double" | "float": options.precision = the declared type of the generated constants */
+const char *spcies_cuda_arithmetic(void);      /* "double" | "float": arithmetic type of the kernels (the reference computes in double  */
+                                               /*   whatever the precision, dec_var.m:16-17; "float" only with float_arithmetic)         */
 int         spcies_cuda_dims(int *nn, int *mm, int *NN);
 long        spcies_cuda_sol_doubles(void);     /* sizeof(sol_<save_name>) / sizeof(double)                */
 int         spcies_cuda_device_count(void);    /* 0 if there is no usable device                          */

@@ -95,6 +95,7 @@ def bench_config(name: str):
         'C2': ('laxMPC_FISTA', 10, dict(tol=1e-4, k_max=1000)),
         'C3': ('equMPC_ADMM', 20, dict(rho=15.0, tol=1e-4, k_max=1000)),
         'C3f': ('equMPC_ADMM', 20, dict(rho=15.0, tol=1e-4, k_max=1000, precision='float')),
+        'C3ff': ('equMPC_ADMM', 20, dict(rho=15.0, tol=1e-4, k_max=1000, precision='float', float_arithmetic=True)),
         'C4': ('ellipMPC_ADMM_soc', 10, dict(rho=15.0, sigma=10.0, tol_p=1e-4, tol_d=1e-4, k_max=1000)),
         'C5a': ('HMPC_SADMM_split', 50, dict(rho=2.0, sigma=20.0, alpha=0.95, tol_p=1e-4, tol_d=1e-4, k_max=1000)),
         'C5b': ('MPCT_EADMM', 50, dict(rho_base=2.0, rho_mult=20.0, tol=1e-4, k_max=1000)),

@@ -4,7 +4,8 @@
 //   SPCIES_SOL_T         generated sol_<save_name> type
 //   SPCIES_SOLVER_STR    "<F>_<method>[_<sub>]"
 //   SPCIES_SAVE_NAME_STR "<save_name>"
-//   SPCIES_PRECISION_STR "double" | "float"
+//   SPCIES_PRECISION_STR "double" | "float"   declared type of the generated constants (options.precision)
+//   SPCIES_ARITH_STR     "double" | "float"   arithmetic type of the kernels
 //   SPCIES_HAS_R         0 | 1
 #pragma once
 
@@ -60,6 +61,7 @@ int spcies_cuda_abi_version(void) { return SPCIES_CUDA_ABI_VERSION; }
 const char *spcies_cuda_solver_name(void) { return SPCIES_SOLVER_STR; }
 const char *spcies_cuda_save_name(void) { return SPCIES_SAVE_NAME_STR; }
 const char *spcies_cuda_precision(void) { return SPCIES_PRECISION_STR; }
+const char *spcies_cuda_arithmetic(void) { return SPCIES_ARITH_STR; }
 int spcies_cuda_dims(int *nn, int *mm, int *NN) {
     if (nn) *nn = nn_;
     if (mm) *mm = mm_;

@@ -83,7 +83,7 @@ def _define_line(row):
 
 def _member_decl(row):
     arr = np.asarray(row.value)
-    ctype = 'int' if _is_int_type(row.type) else 'SPCIES_REAL'
+    ctype = 'int' if _is_int_type(row.type) else 'SPCIES_CONST_REAL'
     if arr.ndim == 0:
         return f'    {ctype} {row.name};'
     dims = ''.join('[%d]' % d for d in arr.shape)
@@ -137,11 +137,19 @@ def emit_text(spec, save_name):
           '// This code is generated by the CUDA platform of spcies_b200 for the Spcies toolbox: '
           'https://github.com/GepocUS/Spcies', '']
 
-    real = 'float' if opts.precision == 'float' else 'double'
+    # precision = 'float': platforms/+C_code/dec_var.m:16-17 only changes the *declared type of the emitted constants*; the
+    # locals of every template stay `double`, i.e. the reference's float solver computes in double on float-rounded constants.
+    # The CUDA platform does the same by default (constants float, arithmetic double: every tensor-core engine applies and the
+    # results match the float-generated reference like the double ones do).  options.solver['float_arithmetic'] = True selects
+    # true single-precision arithmetic instead (one-thread-per-instance kernels; gate 1e-5).
+    const_real = 'float' if opts.precision == 'float' else 'double'
+    real = 'float' if (opts.precision == 'float' and opts.solver.get('float_arithmetic', False)) else 'double'
     cu = [f'// {save_name}.cu -- generated solver: {spec.formulation} {spec.method} {spec.submethod}'.rstrip(),
           f'#include "{save_name}.h"', '',
           f'#define SPCIES_REAL {real}',
-          f'#define SPCIES_PRECISION_STR "{real}"',
+          f'#define SPCIES_CONST_REAL {const_real}',
+          f'#define SPCIES_PRECISION_STR "{const_real}"',
+          f'#define SPCIES_ARITH_STR "{real}"',
           f'#define SPCIES_FUNC {spec.func_name}',
           f'#define SPCIES_SOL_T {sol_t}',
           f'#define SPCIES_SOLVER_STR "{opts.solver_key()}"',
@@ -149,7 +157,7 @@ def emit_text(spec, save_name):
           f'#define SPCIES_HAS_R {has_r}']
     cu += [f'#define {k} {v}' for k, v in switches.items()]
     rows = [r for r in list(spec.constants) + list(spec.variables)]
-    cu += ['#define R_(x) ((SPCIES_REAL)(x))', '', 'struct alignas(16) spcies_consts {']
+    cu += ['#define R_(x) ((SPCIES_CONST_REAL)(x))', '', 'struct alignas(16) spcies_consts {']
     cu += [_member_decl(r) for r in rows]
     cu += ['};', '', 'static const spcies_consts spcies_h_consts = {']
     cu.append(',\n'.join(_member_init(r) for r in rows))

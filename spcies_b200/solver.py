@@ -62,6 +62,8 @@ class CudaSolver:
         self.solver_name = L.spcies_cuda_solver_name().decode()
         self.save_name = L.spcies_cuda_save_name().decode()
         self.precision = L.spcies_cuda_precision().decode()
+        L.spcies_cuda_arithmetic.restype = c_char_p
+        self.arithmetic = L.spcies_cuda_arithmetic().decode()
         nn, mm, NN = c_int(), c_int(), c_int()
         L.spcies_cuda_dims(ctypes.byref(nn), ctypes.byref(mm), ctypes.byref(NN))
         self.n, self.m, self.N = nn.value, mm.value, NN.value

@@ -110,7 +110,7 @@ def test_cuda_emission_text():
     assert '#define nn_ 6' in h and '#define k_max 5000' in h and '#define tol 0.000000100000000' in h
     assert 'SPCIES_CUDA_DECLARE_SOLVER(laxMPC_FISTA, sol_emit_check);' in h
     assert 'double z[80];' in h and 'double lambda[60];' in h
-    assert 'SPCIES_REAL Alpha[9][6][6];' in cu and '#include "MPC_FISTA.cuh"' in cu
+    assert 'SPCIES_CONST_REAL Alpha[9][6][6];' in cu and '#include "MPC_FISTA.cuh"' in cu
     assert 'R_(-1000.000000000000000)' in cu                                   # %1.15f, dec_var.m:259
     cmd = cuda_code.exec_me('/tmp/emit_check.cu')
     assert 'arch=compute_100a,code=sm_100a' in cmd and '-lineinfo' in cmd

@@ -100,16 +100,33 @@ def test_fast_mode_parity(name):
 
 
 def test_float_precision_parity():
-    """precision = 'float' (BASELINE.json configs[2], equMPC ADMM N = 20): the CUDA solver computes in float; the reference
-    generated with precision = 'float' keeps double arithmetic on float-rounded constants (platforms/+C_code/dec_var.m:16-17
-    only changes the declared type of the constants).  Gate (north_star): e_flag identical, u_opt within 1e-5 relative
-    where the iteration counts agree, |dk| <= 1 on all but a handful of instances (float rounding of the residuals moves
-    the exit test; measured 4 of 16384 with |dk| up to 5), u_opt within 10 tol there."""
+    """precision = 'float' (BASELINE.json configs[2], equMPC ADMM N = 20).  The reference generated with precision = 'float' keeps
+    double arithmetic on float-rounded constants (platforms/+C_code/dec_var.m:16-17 only changes the declared type of the
+    constants); so does the CUDA solver by default (constants float, arithmetic double, tensor-core engine): the north-star gate
+    holds as for double -- e_flag identical, |dk| <= 1, u_opt within 1e-5 (measured: 1e-9)."""
+    from _parity import gate
     sol, spec, cfg = prebuilt.get('C3f_equMPC_ADMM')
-    assert sol.precision == 'float'
+    assert sol.precision == 'float' and sol.arithmetic == 'double'
+    batch, kw = _batch(sol, cfg, 16384, seed=41)
+    ur_, kr, er = _ref('C3f_equMPC_ADMM').solve_batch(batch['x0'], batch['xr'], batch['ur'], threads=16)
+    u, k, e, info = sol.solve_batch(batch['x0'], batch['xr'], batch['ur'], arith=ARITH_FAST)
+    gate(spec, u, k, e, ur_, kr, er, tol=1e-9)
+    assert info['sum_k'] == int(k.sum())
+    u, k, e, info = sol.solve_batch(batch['x0'][:2048], batch['xr'][:2048], batch['ur'][:2048], arith=ARITH_EXACT)
+    assert np.array_equal(k, kr[:2048]) and np.array_equal(e, er[:2048])
+    assert np.array_equal(u.view(np.uint64), ur_[:2048].view(np.uint64))        # bit-identical to the float-generated reference
+
+
+def test_float_arithmetic_parity():
+    """options.solver['float_arithmetic']: true single-precision kernels.  Against the float-generated reference (double
+    arithmetic): e_flag identical, u_opt within 1e-5 of the input range where the iteration counts agree, |dk| <= 1 on all but a
+    handful of instances (float rounding of the residuals moves the exit test; measured 4 of 16384 with |dk| up to 5), u_opt
+    within 10 tol there."""
+    sol, spec, cfg = prebuilt.get('C3ff_equMPC_ADMM')
+    assert sol.precision == 'float' and sol.arithmetic == 'float'
     batch, kw = _batch(sol, cfg, 16384, seed=41)
     u, k, e, info = sol.solve_batch(batch['x0'], batch['xr'], batch['ur'], arith=ARITH_FAST)
-    ur_, kr, er = _ref('C3f_equMPC_ADMM').solve_batch(batch['x0'], batch['xr'], batch['ur'], threads=16)
+    ur_, kr, er = _ref('C3ff_equMPC_ADMM').solve_batch(batch['x0'], batch['xr'], batch['ur'], threads=16)
     assert np.array_equal(e, er)
     dk = np.abs(k - kr)
     assert (dk > 1).mean() <= 1e-3 and dk.max() <= 8

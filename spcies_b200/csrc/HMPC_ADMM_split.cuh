@@ -22,9 +22,8 @@
 #include "spcies_dense_mma.cuh"
 #include "spcies_sparse.cuh"
 
-#ifndef NON_SPARSE
-#error "HMPC_ADMM_split.cuh implements the NON_SPARSE (dense M1/M2) path of code_HMPC_ADMM_split_C.c"
-#endif
+// NON_SPARSE (default): dense M1 / M2.  Otherwise (solver option sparse = true): the KKT system [Hh, Gh'; Gh, 0] is solved per
+// iteration through its L D L' factorisation in CSC form (code_HMPC_ADMM_split_C.c:161-164, :193-209; ldl_solve_csc).
 #if defined(COUPLED_CONSTRAINTS) || defined(USE_SOC)
 #error "HMPC_ADMM_split.cuh implements box constraints with diamond-set projections (no COUPLED_CONSTRAINTS / USE_SOC)"
 #endif
@@ -48,9 +47,15 @@ struct Solver {
     typedef SPCIES_REAL real;
     static constexpr int OFF_P = 0;              // primal = (z, s)
     static constexpr int OFF_D = OFF_P + NP;     // dual = (lambda, mu)
+#ifdef NON_SPARSE
     static constexpr int OFF_PH = OFF_D + NP;    // primal_hat
     static constexpr int OFF_QH = OFF_PH + NP;   // q_hat
     static constexpr int OFF_QE = OFF_QH + NP;   // q at x_e  [n]
+#else
+    static constexpr int OFF_PH = OFF_D + NP;    // rhs[nrow_M] = (q_hat, bh) -> (primal_hat, multipliers): z_hat, s_hat are its head
+    static constexpr int OFF_QH = OFF_PH;
+    static constexpr int OFF_QE = OFF_PH + nrow_M;
+#endif
     static constexpr int OFF_QC = OFF_QE + n;    // q at x_c  [n]
     static constexpr int OFF_QU = OFF_QC + n;    // q at u_e  [m]
     static constexpr int OFF_BH = OFF_QU + m;    // bh[0:n]
@@ -115,6 +120,14 @@ struct Solver {
 #pragma unroll 1
             for (int j = 0; j < NS; ++j)
                 s.st(OFF_QH + DIM + j, A::sub(A::mul(rho_, s.ld(OFF_P + DIM + j)), s.ld(OFF_D + DIM + j)));
+#ifndef NON_SPARSE
+            // rhs = (q_hat, bh) with bh[idx_x0[j]] = -A x0;  L D L' rhs = rhs                          :161-164, :193-209
+#pragma unroll 1
+            for (int j = 0; j < nrow_M - NP; ++j) s.st(OFF_PH + NP + j, C->bh[j]);
+#pragma unroll
+            for (int j = 0; j < n; ++j) s.st(OFF_PH + NP + C->idx_x0[j], s.ld(OFF_BH + j));
+            ldl_solve_csc<A>(s, OFF_PH, (int)nrow_M, C->L_val, C->L_row, C->L_col, C->Dinv);
+#else
             // primal_hat = M2 bh - M1 q_hat                                                          :176-188
             real bh[n];
 #pragma unroll
@@ -143,6 +156,7 @@ struct Solver {
                 for (int r = 0; r < RB; ++r)
                     if (i0 + r < NP) s.st(OFF_PH + i0 + r, acc[r]);
             }
+#endif
 
             bool over = false;
             const real as = SYMMETRIC ? A::mul((real)SPCIES_ALPHA, sigma_) : sigma_;   // alpha_SADMM*sigma

@@ -52,6 +52,7 @@ struct Engine {
             S.UBy[g] = g < nm ? (double)C.UBy[g] : 0.0;
         }
         constexpr int NINC = (NW + NC) * 8;
+#ifdef NON_SPARSE
         for (int ot = 0; ot < NO; ++ot)
             for (int o = 0; o < 8; ++o) {
                 const int row = elem_at(ot, o);
@@ -75,6 +76,54 @@ struct Engine {
                     fr[NW * 8 + e] = a;
                 }
             }
+#else
+        // sparse = true: the same map, column by column, through the generated L D L' factors of the KKT matrix: the head of
+        // K^-1 (q_hat; bh) for unit inputs (q_hat = w - q on the z part, bh[idx_x0] = -A x0)       code_HMPC_ADMM_split_C.c:161-209
+        constexpr int NM = nrow_M;
+        ld *rhs = new ld[NM];
+        auto solve = [&]() {
+            for (int i = 0; i < NM; ++i)
+                for (int j = C.L_col[i]; j < C.L_col[i + 1]; ++j) rhs[C.L_row[j]] -= (ld)C.L_val[j] * rhs[i];
+            for (int i = 0; i < NM; ++i) rhs[i] *= (ld)C.Dinv[i];
+            for (int i = NM - 1; i >= 0; --i)
+                for (int j = C.L_col[i]; j < C.L_col[i + 1]; ++j) rhs[i] -= (ld)C.L_val[j] * rhs[C.L_row[j]];
+        };
+        for (int col = 0; col < NINC; ++col) {
+            for (int i = 0; i < NM; ++i) rhs[i] = 0;
+            bool used = false;
+            if (col < NW * 8) {
+                const int e = elem_at(col / 8, col % 8);
+                if (e >= 0) {
+                    rhs[e] = 1;
+                    used = true;
+                }
+            } else {
+                const int e = col - NW * 8;
+                if (e < n) {                          // x0: bh = -A x0;  q_hat -= q,  q_e = -QQ x0, q_c = -QQ x0
+                    for (int j = 0; j < n; ++j) {
+                        rhs[NP + C.idx_x0[j]] = -(ld)C.A[j][e];
+                        rhs[Q0 + j] = (ld)C.QQ[j][e];
+                        rhs[Q0 + 2 * n + j] = (ld)C.QQ[j][e];
+                    }
+                    used = true;
+                } else if (e < 2 * n) {               // xr: q_e = -Te xr
+                    for (int j = 0; j < n; ++j) rhs[Q0 + j] = (ld)C.Te[j][e - n];
+                    used = true;
+                } else if (e < 2 * n + m) {           // ur: q_ue = -Se ur
+                    for (int j = 0; j < m; ++j) rhs[Q0 + 3 * n + j] = (ld)C.Se[j][e - 2 * n];
+                    used = true;
+                }
+            }
+            if (!used) continue;
+            solve();
+            for (int ot = 0; ot < NO; ++ot)
+                for (int o = 0; o < 8; ++o) {
+                    const int row = elem_at(ot, o);
+                    if (row >= 0) F[(size_t)(ot * 8 + o) * NINC + col] = rhs[row];
+                }
+        }
+        delete[] rhs;
+#endif
     }
 
     __device__ static __forceinline__ void init(Lane &, const spcies_consts *C, const Small *, const BatchIO &io, long long inst,

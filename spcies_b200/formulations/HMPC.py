@@ -130,6 +130,35 @@ def compute_HMPC_ADMM_split_ingredients(recipe, box_constraints=True):
     return v
 
 
+def _kkt_ldl(v):
+    """``sparse = true`` (compute_HMPC_ADMM_split_ingredients.m:226-236, :277-286): L D L' of the KKT matrix
+    ``M = [Hh, Gh'; Gh, 0]`` for the QDLDL-style solve of code_HMPC_ADMM_split_C.c:193-209.  The reference calls MATLAB's pivoted
+    ``ldl`` and *assumes* what it needs from the result (D diagonal, no permutation of the primal block, :245-248).  M is
+    quasi-definite (Hh > 0, Gh of full row rank), so the factorisation without pivoting exists with D diagonal -- positive on the
+    primal block, negative on the multiplier block -- and is what is computed here: no permutation at all, ``idx_x0 = 0..n-1``
+    and ``bh`` in its natural order.  The instantiated C template solves the same system with the same L, Dinv."""
+    from .. import sp_utils
+    Hh, Gh = v['Hh'], v['Gh']
+    nh, ng = Hh.shape[0], Gh.shape[0]
+    M = np.block([[Hh, Gh.T], [Gh, np.zeros((ng, ng))]])
+    nM = M.shape[0]
+    L = np.eye(nM)
+    Dg = np.zeros(nM)
+    for j in range(nM):
+        w = L[j, :j] * Dg[:j]
+        Dg[j] = M[j, j] - L[j, :j] @ w
+        if j + 1 < nM:
+            L[j + 1:, j] = (M[j + 1:, j] - L[j + 1:, :j] @ w) / Dg[j]
+    if not (np.all(Dg[:nh] > 0) and np.all(Dg[nh:] < 0)):
+        raise ValueError('HMPC sparse: the KKT matrix is not quasi-definite')
+    err = np.max(np.abs(L @ np.diag(Dg) @ L.T - M))
+    if err > 1e-8 * max(1.0, np.max(np.abs(M))):
+        raise ValueError('HMPC sparse: L D L\' factorisation failed (%.2e)' % err)
+    Lm = L - np.eye(nM)
+    Lm[np.abs(Lm) < 1e-300] = 0.0
+    return dict(L_CSC=sp_utils.full2CSC(Lm), Dinv=1.0 / Dg, idx_x0=np.arange(v['n'], dtype=np.int32), KKT=M)
+
+
 def _cons_split(recipe, symmetric: bool) -> SolverSpec:
     opts = recipe.options
     solver = opts.solver
@@ -137,11 +166,10 @@ def _cons_split(recipe, symmetric: bool) -> SolverSpec:
     if box is None or (isinstance(box, (list, tuple)) and len(box) == 0):
         box = 'E' not in recipe.sys                     # cons_HMPC_ADMM_split_C.m:56-62
     box = bool(box)
-    if solver.get('sparse', False):
-        raise NotImplementedError(
-            "HMPC split solver with sparse=true needs MATLAB's pivoted ldl (compute_HMPC_ADMM_split_ingredients.m:228-233); "
-            "only the default dense (NON_SPARSE) path is generated")
+    sparse = bool(solver.get('sparse', False))
     v = compute_HMPC_ADMM_split_ingredients(recipe, box)
+    if sparse:
+        v.update(_kkt_ldl(v))
     n, m, N, dim, n_s, n_eq = v['n'], v['m'], v['N'], v['dim'], v['n_s'], v['n_eq']
     vopt = var_options(opts)
     vopt_pen = var_options(opts, array=False)
@@ -153,7 +181,7 @@ def _cons_split(recipe, symmetric: bool) -> SolverSpec:
         defs.append(Row('n_y', v['n_y'], True, 'uint', D))
     defs += [Row('NN_', N, True, 'uint', D), Row('dim', dim, True, 'uint', D), Row('n_s', n_s, True, 'uint', D),
              Row('n_eq', n_eq, True, 'uint', D), Row('n_soc', v['n_soc'], True, 'uint', D),
-             Row('NON_SPARSE', 1, True, 'bool', D)]
+             Row('nrow_M', dim + n_eq + 2 * n_s, True, 'uint', D) if sparse else Row('NON_SPARSE', 1, True, 'bool', D)]
     if not box:
         defs.append(Row('COUPLED_CONSTRAINTS', 1, True, 'bool', D))
     defs += [Row('k_max', int(solver['k_max']), True, 'uint', D),
@@ -168,9 +196,16 @@ def _cons_split(recipe, symmetric: bool) -> SolverSpec:
     consts += [Row('A', v['A'], True, prec, vopt), Row('QQ', v['Q'], True, prec, vopt),
                Row('Te', v['Te'], True, prec, vopt), Row('Se', v['Se'], True, prec, vopt),
                Row('LB', v['LB'], True, prec, vopt), Row('UB', v['UB'], True, prec, vopt),
-               Row('LBy', v['LBy'], True, prec, vopt), Row('UBy', v['UBy'], True, prec, vopt),
-               Row('M1', v['M1'], True, prec, vopt)]
-    if v['use_soc']:
+               Row('LBy', v['LBy'], True, prec, vopt), Row('UBy', v['UBy'], True, prec, vopt)]
+    if sparse:                                          # cons_HMPC_ADMM_split_C.m:136-142
+        consts += [Row('L_val', v['L_CSC'].val, True, prec, vopt), Row('L_col', v['L_CSC'].col, True, 'int', vopt),
+                   Row('L_row', v['L_CSC'].row, True, 'int', vopt), Row('Dinv', v['Dinv'], True, prec, vopt),
+                   Row('idx_x0', v['idx_x0'], True, 'int', vopt)]
+    else:
+        consts.append(Row('M1', v['M1'], True, prec, vopt))
+    if sparse:
+        pass
+    elif v['use_soc']:
         consts.append(Row('M2', v['M2'], True, prec, vopt))
         defs.append(Row('dim_M2', n_eq + n_s, True, prec, D))
     else:

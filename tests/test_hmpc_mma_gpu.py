@@ -31,7 +31,8 @@ def _gate(spec, u, k, e, ur_, kr, er):
         assert _abs_err(u[~same], ur_[~same]) <= 10 * float(spec.define('tol_p'))
 
 
-@pytest.mark.parametrize('name,B', [('T_HMPC_ADMM_split', 1500), ('T_HMPC_SADMM_split', 1500), ('C5a_HMPC_SADMM_split', 160)])
+@pytest.mark.parametrize('name,B', [('T_HMPC_ADMM_split', 1500), ('T_HMPC_SADMM_split', 1500), ('T_HMPC_SADMM_split_sparse', 600),
+                                    ('C5a_HMPC_SADMM_split', 160)])
 def test_hmpc_mma_engine_parity(name, B):
     sol, spec, cfg = prebuilt.get(name)
     batch = sysmodel.synthetic_batch(cfg['sys'], B, seed=71)

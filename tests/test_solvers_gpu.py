@@ -12,7 +12,8 @@ pytestmark = pytest.mark.gpu
 GOLD = {'T_laxMPC_FISTA': ('laxMPC_FISTA', 'z'), 'T_equMPC_FISTA': ('equMPC_FISTA', 'z'),
         'T_laxMPC_ADMM': ('laxMPC_ADMM', 'z'), 'T_equMPC_ADMM': ('equMPC_ADMM', 'z'),
         'T_ellipMPC_ADMM': ('ellipMPC_ADMM', 'z'), 'T_ellipMPC_ADMM_soc': ('ellipMPC_ADMM_soc', 'z'),
-        'T_MPCT_EADMM': ('MPCT_EADMM', 'z1'), 'T_HMPC_ADMM_split': None, 'T_HMPC_SADMM_split': None}
+        'T_MPCT_EADMM': ('MPCT_EADMM', 'z1'), 'T_HMPC_ADMM_split': None, 'T_HMPC_SADMM_split': None,
+        'T_HMPC_SADMM_split_sparse': None}      # sparse = true: the KKT L D L' branch (code_HMPC_ADMM_split_C.c:193-209)
 TEST_SOLVERS = list(GOLD)
 BATCH_SOLVERS = TEST_SOLVERS + ['C2_laxMPC_FISTA', 'C3_equMPC_ADMM', 'C4_ellipMPC_ADMM_soc', 'T_equMPC_ADMM_vb']   # _vb: per-stage bounds
 LONG_HORIZON = ['C5a_HMPC_SADMM_split', 'C5b_MPCT_EADMM']      # N = 50: per-instance state in the global scratch

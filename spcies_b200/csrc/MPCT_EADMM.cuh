@@ -179,7 +179,7 @@ struct Solver {
                 for (int j = 0; j < n; ++j) {
                     real r = A::mul(C->H3i[l + 1][j], qb[j]);
 #pragma unroll
-                    for (int i = 0; i < nm; ++i) r = A::nmsub(r, A::mul(C->AB[j][i], C->H3i[l][i]), qa[i]);
+                    for (int i = 0; i < nm; ++i) r = A::nmsub(r, cprod<A>(C->AB[j][i], C->H3i[l][i]), qa[i]);
                     mu[j] = r;
                 }
                 fwd_block(mu, mprev, l, l == 0);

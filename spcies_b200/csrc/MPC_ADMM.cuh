@@ -248,7 +248,7 @@ struct Solver {
             for (int j = 0; j < n; ++j) {
                 real r = A::madd(-s.ld(OFF_B + j), C->Hi[0][j], zc[j]);                  // Hi[0][j]*z[0][j] - b[j]
 #pragma unroll
-                for (int i = 0; i < m; ++i) r = A::nmsub(r, A::mul(C->AB[j][n + i], C->Hi_0[i]), z0h[i]);
+                for (int i = 0; i < m; ++i) r = A::nmsub(r, cprod<A>(C->AB[j][n + i], C->Hi_0[i]), z0h[i]);
                 mu[j] = r;
             }
             fwd_block(mu, mprev, 0, true);
@@ -267,7 +267,7 @@ struct Solver {
                 for (int j = 0; j < n; ++j) {
                     real r = A::mul(C->Hi[l][j], zc[j]);
 #pragma unroll
-                    for (int i = 0; i < nm; ++i) r = A::nmsub(r, A::mul(C->AB[j][i], C->Hi[l - 1][i]), zp[i]);
+                    for (int i = 0; i < nm; ++i) r = A::nmsub(r, cprod<A>(C->AB[j][i], C->Hi[l - 1][i]), zp[i]);
                     mu[j] = r;
                 }
                 fwd_block(mu, mprev, l, false);
@@ -307,7 +307,7 @@ struct Solver {
                 for (int i = 0; i < n; ++i) r = A::madd(r, C->Hi_N[j][i], zN[i]);
 #endif
 #pragma unroll
-                for (int i = 0; i < nm; ++i) r = A::nmsub(r, A::mul(C->AB[j][i], C->Hi[N - 2][i]), zp[i]);
+                for (int i = 0; i < nm; ++i) r = A::nmsub(r, cprod<A>(C->AB[j][i], C->Hi[N - 2][i]), zp[i]);
 #if SPCIES_TERMINAL == 0
                 r = A::sub(r, s.ld(OFF_QT + j));                                         // - xr[j]
 #endif

@@ -45,6 +45,7 @@ constexpr size_t MMA_STATE_PER_WARP = (size_t)2 * MMA_NBLK * 32 * sizeof(double2
 struct alignas(16) MmaTables {
     // by column (spcies_mma.cuh: MmaLayout); matrices row-major [output column][input column]
     double NAB[64];           // -[A B]   (out x, in z)
+    double NAB0[64];          // the same for block 0, whose state columns carry -x0 (see fill_mma_tables: float constants)
     double ABt[64];           //  [A B]'  (out z, in x)
     double2 FWa[N][32], BWa[N][32];
     double FWb[N][32], BWb[N][32];
@@ -99,7 +100,18 @@ static inline bool fill_mma_tables(const spcies_consts &C, MmaTables &T) {
     }
     for (int oc = 0; oc < 8; ++oc)
         for (int ic = 0; ic < 8; ++ic) {
-            if (L::x_at(oc) >= 0 && L::z_at(ic) >= 0) T.NAB[oc * 8 + ic] = -(double)C.AB[L::x_at(oc)][L::z_at(ic)];
+            if (L::x_at(oc) >= 0 && L::z_at(ic) >= 0) {
+                // r_b = s_{b+1} - [A B] s_b with s_b = Hi o q_hat_b.  The templates evaluate `AB[j][i]*Hi[l-1][i]*z[l-1][i]`
+                // (code_equMPC_ADMM_C.c:340): with float constants the first product is rounded to float, so the fragment
+                // applied to s_b is that product divided by Hi again; b = -A x0 (:272) takes the plain entries (block 0).
+                const int x = L::x_at(oc), z = L::z_at(ic);
+                T.NAB0[oc * 8 + ic] = T.NAB[oc * 8 + ic] = -(double)C.AB[x][z];
+                if (sizeof(C.AB[0][0]) == 4) {
+                    const double eff = -cprod_host(C.AB[x][z], C.Hi[0][z]) / (double)C.Hi[0][z];
+                    T.NAB[oc * 8 + ic] = eff;
+                    if (z >= n) T.NAB0[oc * 8 + ic] = eff;
+                }
+            }
             if (L::z_at(oc) >= 0 && L::x_at(ic) >= 0) T.ABt[oc * 8 + ic] = (double)C.AB[L::x_at(ic)][L::z_at(oc)];
         }
 #if SPCIES_TERMINAL != 0
@@ -242,6 +254,7 @@ __global__ void __launch_bounds__(MMA_BLOCK, 1) admm_mma_kernel(const BatchIO io
                 sp[0] = xs[0] ? nx0[0] : hi[0] * qh0;           // block 0: the state columns carry -x0 (r_0 = ... - b, b = -A x0)
                 sp[1] = xs[1] ? nx0[1] : hi[1] * qh1;
             }
+            const double2 nab0 = reinterpret_cast<const double2 *>(T->NAB0)[lane];
             constexpr int GRP = 5;   // blocks per group: their r.h.s. products are independent and issued back to back
 #pragma unroll
             for (int b0 = 0; b0 < N; b0 += GRP) {
@@ -279,10 +292,10 @@ __global__ void __launch_bounds__(MMA_BLOCK, 1) admm_mma_kernel(const BatchIO io
                 }
 #pragma unroll
                 for (int j = 0; j < GRP; ++j)
-                    if (b0 + j < N) dmma(e[j][0], e[j][1], s[j][0], nab.x, s[j + 1][0], s[j + 1][1]);
+                    if (b0 + j < N) dmma(e[j][0], e[j][1], s[j][0], b0 + j == 0 ? nab0.x : nab.x, s[j + 1][0], s[j + 1][1]);
 #pragma unroll
                 for (int j = 0; j < GRP; ++j)
-                    if (b0 + j < N) dmma(r[j][0], r[j][1], s[j][1], nab.y, e[j][0], e[j][1]);
+                    if (b0 + j < N) dmma(r[j][0], r[j][1], s[j][1], b0 + j == 0 ? nab0.y : nab.y, e[j][0], e[j][1]);
 #pragma unroll
                 for (int j = 0; j < GRP; ++j)
                     if (b0 + j < N) dmma(e[j][0], e[j][1], r[j][0], T->FWa[b0 + j][lane].x, 0.0, 0.0);

@@ -66,6 +66,17 @@ template <> struct Arith<float, true> {
     static __device__ __forceinline__ T sqrt(T a) { return __fsqrt_rn(a); }
 };
 
+// Product of two generated constants as the C templates evaluate it: in the constants' own type, then promoted.  With
+// precision = 'float' the constants are `const static float` and `AB[j][i]*Hi[l-1][i]*z[l-1][i]` (code_equMPC_ADMM_C.c:340) is
+// a float product times a double; with double constants this is the plain product of the arithmetic policy.
+template <class A> __device__ __forceinline__ typename A::T cprod(double a, double b) { return A::mul((typename A::T)a, (typename A::T)b); }
+template <class A> __device__ __forceinline__ typename A::T cprod(float a, float b) { return (typename A::T)__fmul_rn(a, b); }
+static inline double cprod_host(double a, double b) { return a * b; }
+static inline double cprod_host(float a, float b) {
+    volatile float p = a * b;
+    return (double)p;
+}
+
 template <typename T> __device__ __forceinline__ T clip(T v, T lb, T ub) {
     v = (v > lb) ? v : lb;   // maximum between v and the lower bound
     v = (v > ub) ? ub : v;   // minimum between v and the upper bound

@@ -236,6 +236,7 @@ class Ctx:
                 dist.init_process_group('nccl', device_id=torch.device('cuda', self.local_rank), timeout=datetime.timedelta(minutes=30))
                 dist.barrier()
                 torch.cuda.synchronize(self.local_rank)
+                self.host_group = dist.new_group(backend='gloo', timeout=datetime.timedelta(minutes=30))     # host-side waits that leave the GPUs idle (host_barrier)
             finally:
                 sys.stdout.flush()
                 os.dup2(saved_stdout, 1)
@@ -248,6 +249,13 @@ class Ctx:
         if self.world > 1:
             self.dist.barrier()
         self.torch.cuda.synchronize(self.dev)
+
+    def host_barrier(self):
+        """Barrier on the host only: waiting ranks launch nothing (an NCCL barrier keeps a kernel spinning on every waiting GPU,
+        which would time-slice with another process's work on that GPU)."""
+        self.torch.cuda.synchronize(self.dev)
+        if self.world > 1:
+            self.dist.barrier(group=self.host_group)
 
     def max_over_ranks(self, x):
         from spcies_b200.sharding import reduce_scalar
@@ -491,6 +499,7 @@ def c5_sharded(cx, config_name, total, one_process=True):
     # ---- the product API's own multi-GPU path: one process, one call, n_devices = world
     if one_process and cx.world > 1:
         res = None
+        cx.host_barrier()          # ranks > 0 now wait on the host: rank 0 drives every GPU of the node from one process
         if cx.rank == 0:
             try:
                 allp = [sysmodel.synthetic_batch(cfg['sys'], chunk, seed=200 + c) for c in range(per * cx.world)]
@@ -512,7 +521,7 @@ def c5_sharded(cx, config_name, total, one_process=True):
                               'thread per device inside the library), wall clock of the call' % cx.world}
             except Exception as ex:                                  # pragma: no cover
                 res = {'error': str(ex)}
-        cx.barrier()
+        cx.host_barrier()
         out['one_process_n_devices'] = res
     return out
 

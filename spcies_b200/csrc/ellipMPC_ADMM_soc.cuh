@@ -165,11 +165,21 @@ struct Solver {
 };
 
 #include "ellipMPC_ADMM_soc_mma.cuh"
+#include "ellipMPC_ADMM_soc_band.cuh"
 
-// Host-side traits: the scalar skeleton plus the tensor-core engine (FAST arithmetic, no debug payload)
+// Host-side traits: the scalar skeleton plus the two tensor-core engines (FAST arithmetic, no debug payload): the structured
+// one (ellipMPC_ADMM_soc_band.cuh) when the generated constants have its structure, else the dense map (ellipMPC_ADMM_soc_mma.cuh;
+// SPCIES_CUDA_SOC_ENGINE=dense in the environment forces it)
 struct Traits : PolicyTraits<Solver> {
     typedef PolicyTraits<Solver> Base;
-    static size_t blob_bytes() { return HAS_MMA ? MMA_OFFSET + SMALL_BYTES + FRAG_BYTES : Base::blob_bytes(); }
+    static bool &band_ok() {
+        static bool ok = false;
+        return ok;
+    }
+    static size_t blob_bytes() {
+        if (HAS_BAND) return BAND_OFFSET + BAND_BYTES;
+        return HAS_MMA ? MMA_OFFSET + SMALL_BYTES + FRAG_BYTES : Base::blob_bytes();
+    }
     static void fill_blob(void *dst) {
         memset(dst, 0, blob_bytes());
         Base::fill_blob(dst);
@@ -179,25 +189,46 @@ struct Traits : PolicyTraits<Solver> {
             memcpy((char *)dst + MMA_OFFSET, S, sizeof *S);
             delete S;
         }
+        if constexpr (HAS_BAND) {
+            BandTables *B = new BandTables;
+            band_ok() = fill_band_tables(spcies_h_consts, *B);
+            memcpy((char *)dst + BAND_OFFSET, B, sizeof *B);
+            delete B;
+        }
     }
     static bool use_mma(int arith, const BatchIO &io) {
-        if constexpr (!HAS_MMA) return false;
-        return arith != SPCIES_CUDA_ARITH_EXACT && io.sol == nullptr && io.engine != SPCIES_CUDA_ENGINE_SCALAR && io.LB == nullptr;
+        if constexpr (!HAS_MMA && !HAS_BAND) return false;
+        return arith != SPCIES_CUDA_ARITH_EXACT && io.sol == nullptr && io.engine != SPCIES_CUDA_ENGINE_SCALAR && io.LB == nullptr &&
+               (HAS_MMA || use_band());
+    }
+    static bool use_band() {
+        if constexpr (!HAS_BAND) return false;
+        const char *e = getenv("SPCIES_CUDA_SOC_ENGINE");
+        const bool dense = e != nullptr && strcmp(e, "dense") == 0 && HAS_MMA;
+        return band_ok() && !dense;
     }
     static bool uses_scratch(int arith, const BatchIO &io) { return !use_mma(arith, io); }
     static void engine_shape(int arith, const BatchIO &io, int &block, size_t &smem, int &ipb) {
         ipb = block;
         if (use_mma(arith, io)) {
-            block = MMA_BLOCK;
-            smem = MMA_SMEM;
-            ipb = MMA_IPB;
+            block = use_band() ? BAND_BLOCK : MMA_BLOCK;
+            smem = use_band() ? BAND_SMEM : MMA_SMEM;
+            ipb = use_band() ? BAND_IPB : MMA_IPB;
         }
     }
     static cudaError_t launch(int arith, bool varb, int grid, int block, size_t smem, cudaStream_t s, const BatchIO &io,
                               const void *dc, void *scratch) {
         if (io.engine == SPCIES_CUDA_ENGINE_MMA && !use_mma(arith, io)) return cudaErrorNotSupported;
-        if constexpr (HAS_MMA) {
-            if (use_mma(arith, io)) {
+        if (use_mma(arith, io)) {
+            if constexpr (HAS_BAND) {
+                if (use_band()) {
+                    cudaError_t e = cudaFuncSetAttribute(soc_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BAND_SMEM);
+                    if (e != cudaSuccess) return e;
+                    soc_band_kernel<<<grid, BAND_BLOCK, BAND_SMEM, s>>>(io, (const unsigned char *)dc);
+                    return cudaGetLastError();
+                }
+            }
+            if constexpr (HAS_MMA) {
                 cudaError_t e = cudaFuncSetAttribute(soc_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MMA_SMEM);
                 if (e != cudaSuccess) return e;
                 soc_mma_kernel<<<grid, MMA_BLOCK, MMA_SMEM, s>>>(io, (const unsigned char *)dc);
@@ -207,8 +238,11 @@ struct Traits : PolicyTraits<Solver> {
         return Base::launch(arith, varb, grid, block, smem, s, io, dc, scratch);
     }
     static cudaError_t attributes(int arith, bool varb, cudaFuncAttributes *a) {
-        if constexpr (HAS_MMA) {
-            if (arith != SPCIES_CUDA_ARITH_EXACT) return cudaFuncGetAttributes(a, soc_mma_kernel);
+        if (arith != SPCIES_CUDA_ARITH_EXACT) {
+            if constexpr (HAS_BAND) {
+                if (use_band()) return cudaFuncGetAttributes(a, soc_band_kernel);
+            }
+            if constexpr (HAS_MMA) return cudaFuncGetAttributes(a, soc_mma_kernel);
         }
         return Base::attributes(arith, varb, a);
     }

@@ -1,6 +1,8 @@
-"""GPU parity of the tensor-core (DMMA) engine of the ellipMPC ADMM_soc solver (spcies_b200/csrc/ellipMPC_ADMM_soc_mma.cuh):
-the reference's CSR / CSC-LDL chain folded into one dense linear map (formed on the host in extended precision from the
-generated sparse constants) and applied as a batched FP64 MMA GEMM, SOC projection across the 4 lanes of an instance.
+"""GPU parity of the tensor-core (DMMA) engines of the ellipMPC ADMM_soc solver: the structured one
+(spcies_b200/csrc/ellipMPC_ADMM_soc_band.cuh: W is block tridiagonal with N + 1 blocks once the two rows that pin t are taken
+out, so the iteration is the equMPC ADMM engine with a dense terminal block and a cone block) and the dense one
+(spcies_b200/csrc/ellipMPC_ADMM_soc_mma.cuh: the reference's CSR / CSC-LDL chain folded into one dense linear map applied as a
+batched FP64 MMA GEMM; kept for the shapes / structures the first does not take, SPCIES_CUDA_SOC_ENGINE=dense forces it).
 Gate (BASELINE.json north_star): e_flag identical, |dk| <= 1, u_opt <= 1e-9 relative on converged instances, against the
 instantiated reference C solver (oracle/_ref)."""
 import numpy as np
@@ -45,6 +47,23 @@ def test_soc_mma_engine_parity(name, B):
     _gate(spec, u2, k2, e2, ur_[:nb], kr[:nb], er[:nb])
     u3, k3, e3, _ = sol.solve_batch(batch['x0'], batch['xr'], batch['ur'], r=batch['r'])       # default engine = MMA
     assert np.array_equal(u3.view(np.uint64), u.view(np.uint64)) and np.array_equal(k3, k) and np.array_equal(e3, e)
+
+
+@pytest.mark.parametrize('name', ['T_ellipMPC_ADMM_soc', 'C4_ellipMPC_ADMM_soc'])
+def test_soc_structured_and_dense_engines_agree(name, monkeypatch):
+    """Both engines against the reference on the same batch; the default is the structured one (256 threads per CTA; the
+    dense one sizes its CTA by the shared memory its fragment table leaves)."""
+    sol, spec, cfg = prebuilt.get(name)
+    batch = sysmodel.synthetic_batch(cfg['sys'], 3000, seed=84, with_r=True)
+    ur_, kr, er = _ref(name).solve_batch(batch['x0'], batch['xr'], batch['ur'], r=batch['r'], threads=16)
+    u, k, e, info = sol.solve_batch(batch['x0'], batch['xr'], batch['ur'], r=batch['r'], engine=ENGINE_MMA)
+    _gate(spec, u, k, e, ur_, kr, er)
+    monkeypatch.setenv('SPCIES_CUDA_SOC_ENGINE', 'dense')
+    ud, kd, ed, infod = sol.solve_batch(batch['x0'], batch['xr'], batch['ur'], r=batch['r'], engine=ENGINE_MMA)
+    monkeypatch.delenv('SPCIES_CUDA_SOC_ENGINE')
+    _gate(spec, ud, kd, ed, ur_, kr, er)
+    assert info['block_threads'] == 256 and infod['block_threads'] != 256
+    assert np.array_equal(e, ed) and np.max(np.abs(k - kd)) <= 1
 
 
 def test_soc_mma_ragged_batches():

@@ -400,7 +400,16 @@ template <class Traits> struct Runtime {
             }
             if (two_phase || ncaps > 0) {
                 long long need = (long long)grid * block;
-                if (ncaps > 0) need = std::max<long long>(4LL * grid * ipb, B / 16 + 1024);
+                if (ncaps > 0) {
+                    // records of the instances that outlive a cap (C2: 1.5 % at 96 iterations, 25 % at 32); instances that find the
+                    // park full run on to the end in place.  SPCIES_CUDA_PARK_DIV: capacity = B / div (development knob)
+                    static const long long div = [] {
+                        const char *e = getenv("SPCIES_CUDA_PARK_DIV");
+                        const long long v = e ? atoll(e) : 0;
+                        return v >= 1 ? v : 16;
+                    }();
+                    need = std::max<long long>(4LL * grid * ipb, B / div + 1024);
+                }
                 if (need > c.cap_park) {
                     if (c.d_park) SPCIES_CK(cudaFree(c.d_park));
                     if (c.d_park2) SPCIES_CK(cudaFree(c.d_park2));

@@ -51,7 +51,7 @@ def test_soc_mma_engine_parity(name, B):
 
 @pytest.mark.parametrize('name', ['T_ellipMPC_ADMM_soc', 'C4_ellipMPC_ADMM_soc'])
 def test_soc_structured_and_dense_engines_agree(name, monkeypatch):
-    """Both engines against the reference on the same batch; the default is the structured one (256 threads per CTA; the
+    """Both engines against the reference on the same batch; the default is the structured one (512 threads per CTA; the
     dense one sizes its CTA by the shared memory its fragment table leaves)."""
     sol, spec, cfg = prebuilt.get(name)
     batch = sysmodel.synthetic_batch(cfg['sys'], 3000, seed=84, with_r=True)
@@ -62,7 +62,7 @@ def test_soc_structured_and_dense_engines_agree(name, monkeypatch):
     ud, kd, ed, infod = sol.solve_batch(batch['x0'], batch['xr'], batch['ur'], r=batch['r'], engine=ENGINE_MMA)
     monkeypatch.delenv('SPCIES_CUDA_SOC_ENGINE')
     _gate(spec, ud, kd, ed, ur_, kr, er)
-    assert info['block_threads'] == 256 and infod['block_threads'] != 256
+    assert info['block_threads'] == 512 and infod['block_threads'] != 512
     assert np.array_equal(e, ed) and np.max(np.abs(k - kd)) <= 1
 
 

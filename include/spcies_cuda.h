@@ -77,6 +77,9 @@ extern "C" {
 #define SPCIES_CUDA_ENGINE_AUTO   0
 #define SPCIES_CUDA_ENGINE_SCALAR 1
 #define SPCIES_CUDA_ENGINE_MMA    2  /* fail with cudaErrorNotSupported instead of falling back to SCALAR */
+#define SPCIES_CUDA_ENGINE_SINGLE 3 /* latency engine of the FISTA solvers: one CTA per instance, dense W^-1 (MPC_FISTA_single.cuh);   */
+                                    /* AUTO uses it for host-buffer calls of at most 64 instances (the reference's single-instance    */
+                                    /* symbol is one); fails with SPCIES_CUDA_EUNSUPPORTED where it cannot run                        */
 
 /* Options of a batched call.  Zero-initialise, then set what you need; NULL means all defaults. */
 typedef struct {
@@ -91,7 +94,7 @@ typedef struct {
     int grid_blocks;         /* 0: one CTA per SM */
     int tail_mode;           /* SPCIES_CUDA_TAIL_AUTO (default) | _SINGLE | _TWO_PHASE, see above */
     int tail_grace;          /* iterations an instance may still run after the queue ran dry before it is parked (0: 32) */
-    int engine;              /* SPCIES_CUDA_ENGINE_AUTO (default) | _SCALAR | _MMA, see above */
+    int engine;              /* SPCIES_CUDA_ENGINE_AUTO (default) | _SCALAR | _MMA | _SINGLE, see above */
     int tail_caps[3];        /* increasing iteration caps of SPCIES_CUDA_TAIL_CAPS, 0-terminated (all 0: 96, 320) */
     int warm_start;          /* closed loop: 0 = cold start; 1 = start every sampling time from the dual point of the previous one  */
                              /*   (FISTA solvers: the `lambda` argument of platforms/Matlab/spcies_laxMPC_FISTA_solver.m:161-164);  */

@@ -707,6 +707,7 @@ __global__ void __launch_bounds__(BLOCK, 1) fista_kernel(const BatchIO io, const
 }
 
 #include "MPC_FISTA_mma.cuh"
+#include "MPC_FISTA_single.cuh"
 
 struct Traits {
     static constexpr int NN = n, MM = m, NMM = nm;
@@ -722,7 +723,7 @@ struct Traits {
     typedef spcies_consts Consts;
     static const Consts &host_consts() { return spcies_h_consts; }
     // device constant blob: the generated constants + the derived FAST-mode blocks
-    static size_t blob_bytes() { return HAS_MMA ? TOTAL_BLOB_BYTES : BLOB_BYTES; }
+    static size_t blob_bytes() { return (HAS_MMA ? TOTAL_BLOB_BYTES : BLOB_BYTES) + (HAS_SINGLE ? SINGLE_BYTES : 0); }
     static void fill_blob(void *dst) {
         memset(dst, 0, blob_bytes());
         memcpy(dst, &spcies_h_consts, sizeof spcies_h_consts);
@@ -736,6 +737,49 @@ struct Traits {
             delete T;
         }
         delete D;
+        if constexpr (HAS_SINGLE) {
+            SingleTables *S = new SingleTables;
+            fill_single_tables(spcies_h_consts, *S);
+            memcpy((char *)dst + SINGLE_OFFSET, S, sizeof *S);
+            delete S;
+        }
+    }
+    // latency engine (one CTA per instance) for small host-buffer calls: FAST arithmetic, no debug payload
+    static bool single_engine(int arith, const BatchIO &io) {
+        if constexpr (!HAS_SINGLE) return false;
+        return arith != SPCIES_CUDA_ARITH_EXACT && io.sol == nullptr &&
+               (io.engine == SPCIES_CUDA_ENGINE_AUTO || io.engine == SPCIES_CUDA_ENGINE_SINGLE);
+    }
+    static cudaError_t launch_single(bool varb, int grid, cudaStream_t s, const BatchIO &io, const void *dc, int &block, size_t &smem,
+                                     const double *hx0, const double *hxr, const double *hur) {
+        if constexpr (HAS_SINGLE) {
+            block = SG_BLOCK;
+            smem = SINGLE_SMEM;
+            SingleArgs a;
+            a.count = 0;
+            if (hx0 != nullptr && grid <= SG_NARG) {        // the inputs of a few instances travel with the launch
+                a.count = grid;
+                memcpy(a.x0, hx0, (size_t)grid * n * sizeof(double));
+                memcpy(a.xr, hxr, (size_t)grid * n * sizeof(double));
+                memcpy(a.ur, hur, (size_t)grid * m * sizeof(double));
+            }
+            if (varb) fista_single_kernel<true><<<grid, SG_BLOCK, SINGLE_SMEM, s>>>(io, (const unsigned char *)dc, a);
+            else fista_single_kernel<false><<<grid, SG_BLOCK, SINGLE_SMEM, s>>>(io, (const unsigned char *)dc, a);
+            return cudaGetLastError();
+        }
+        return cudaErrorNotSupported;
+    }
+    // the lingering server of the single-instance symbol (MPC_FISTA_single.cuh); mb = device address of the mapped mailbox
+    static constexpr bool HAS_SERVER = HAS_SINGLE;
+    static cudaError_t launch_server(cudaStream_t s, const void *dc, void *mb, unsigned int seq0, unsigned long long linger_ns, int &block,
+                                     size_t &smem) {
+        if constexpr (HAS_SINGLE) {
+            block = SG_BLOCK;
+            smem = SINGLE_SMEM;
+            fista_server_kernel<<<1, SG_BLOCK, SINGLE_SMEM, s>>>((const unsigned char *)dc, (Mailbox *)mb, seq0, linger_ns);
+            return cudaGetLastError();
+        }
+        return cudaErrorNotSupported;
     }
     // which engine runs a call: the tensor-core kernel for FAST arithmetic without debug payload, unless the caller
     // asked for the scalar one (spcies_batch_opts.engine)
@@ -794,6 +838,7 @@ struct Traits {
                               const void *dc, void *) {
         const bool ex = arith == SPCIES_CUDA_ARITH_EXACT;
         if (io.engine == SPCIES_CUDA_ENGINE_MMA && !use_mma(arith, io)) return cudaErrorNotSupported;
+        if (io.engine == SPCIES_CUDA_ENGINE_SINGLE) return cudaErrorNotSupported;      // only through launch_single (small host-buffer calls)
         if constexpr (HAS_MMA) {
             if (use_mma(arith, io)) {
                 const bool bulk = block == MMA_BLOCK_BULK && MMA_BLOCK_BULK != MMA_BLOCK;

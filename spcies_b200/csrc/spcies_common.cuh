@@ -105,6 +105,12 @@ template <class CT> __device__ __forceinline__ double eng_u(const CT *C, const d
 template <class CT> __device__ __forceinline__ double eng_u_out(const CT *C, double u, int j) {
     return __dadd_rn(__dmul_rn(u, (double)C->scaling_i_u[j]), (double)C->OpPoint_u[j]);
 }
+template <class CT> __device__ __forceinline__ double eng_x_value(const CT *C, double v, int i) {
+    return __dmul_rn((double)C->scaling_x[i], __dsub_rn(v, (double)C->OpPoint_x[i]));
+}
+template <class CT> __device__ __forceinline__ double eng_u_value(const CT *C, double v, int i) {
+    return __dmul_rn((double)C->scaling_u[i], __dsub_rn(v, (double)C->OpPoint_u[i]));
+}
 #else
 template <class CT> __device__ __forceinline__ double eng_x(const CT *, const double *a, long long inst, int n_, int i) {
     return a[inst * n_ + i];
@@ -113,6 +119,8 @@ template <class CT> __device__ __forceinline__ double eng_u(const CT *, const do
     return a[inst * m_ + i];
 }
 template <class CT> __device__ __forceinline__ double eng_u_out(const CT *, double u, int) { return u; }
+template <class CT> __device__ __forceinline__ double eng_x_value(const CT *, double v, int) { return v; }
+template <class CT> __device__ __forceinline__ double eng_u_value(const CT *, double v, int) { return v; }
 #endif
 
 // ------------------------------------------------------------------------------------------------
@@ -197,7 +205,30 @@ struct BatchIO {
     int cl_warm;                      // 1: the dual point of the previous sampling time is the starting point of the next
     long long cl_ld;                  // instances per sampling time in the trajectory arrays
     double *cl_x;                     // [cl_steps + 1][cl_ld][nn_] or nullptr
+    // latency engines (Traits::single_engine): per-instance completion flags in mapped host memory, or nullptr
+    unsigned int *done;               // [B]: set to done_seq (after a system-wide fence) once u / k / e of the instance are written
+    unsigned int done_seq;
 };
+// Mailbox of a lingering single-instance server kernel (Traits::HAS_SERVER, MPC_FISTA_single.cuh), in mapped pinned host memory.
+// Host -> device: 64-byte lines of seven doubles + (seq, cmd); the payload is (x0[NN], xr[NN], ur[MM]) and a request is complete
+// when every line carries the new sequence number (the host writes a line's doubles, then -- after a store fence -- its seq; a
+// PCIe read returns a consistent snapshot of a 64-byte line).  cmd of line 0 != 0 tells the server to exit.
+// Device -> host: one line with the results and the sequence number they answer (written after a system-wide fence); `alive` is
+// set by the host before a launch and cleared by the kernel as its last action.
+template <int NN, int MM> struct alignas(64) SingleMailbox {
+    static constexpr int NL = (2 * NN + MM + 6) / 7;
+    struct alignas(64) Line {
+        double v[7];
+        unsigned int seq, cmd;
+    } in[NL];
+    struct alignas(64) Out {
+        double u[MM < 5 ? 5 : MM];
+        int k, e;
+        unsigned int seq, pad;
+    } out;
+    alignas(64) unsigned int alive;
+};
+
 constexpr int QUEUE_WORDS = 16;   // [8]: number of instances whose inputs have arrived (pipelined host->device copies)
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {

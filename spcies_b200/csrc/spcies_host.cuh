@@ -16,6 +16,7 @@
 //   static cudaError_t attributes(int arith, bool varb, cudaFuncAttributes *a);
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -56,6 +57,10 @@ struct DeviceCtx {
     unsigned long long *h_ready = nullptr;       // pinned: watermark values copied to d_queue[8] after every chunk
     double *h_stage = nullptr;                   // pinned, device-mapped staging of the small-batch path (zero-copy in / out)
     double *d_stage = nullptr;                   // its device address
+    unsigned int small_seq = 0;                  // call counter of the latency engine (value of its completion flags)
+    void *h_mb = nullptr, *d_mb = nullptr;       // mailbox of the lingering single-instance server (mapped pinned host memory)
+    unsigned int srv_seq = 0;                    // sequence number of the last request posted to it
+    cudaStream_t srv_stream = nullptr;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     void *d_consts = nullptr;
     unsigned long long *d_queue = nullptr;
@@ -202,6 +207,11 @@ template <class Traits> struct Runtime {
             cudaStreamDestroy(c.copy_stream);
             cudaFreeHost(c.h_ready);
             if (c.h_stage) cudaFreeHost(c.h_stage);
+            if (c.h_mb) {
+                stop_server(c, true);
+                cudaStreamDestroy(c.srv_stream);
+                cudaFreeHost(c.h_mb);
+            }
             c = DeviceCtx();
         }
     }
@@ -237,6 +247,81 @@ template <class Traits> struct Runtime {
         return on;
     }
 
+    // ---- lingering server of the single-instance symbol (Traits::HAS_SERVER) --------------------------------------------------
+    typedef SingleMailbox<Traits::NN, Traits::MM> Mailbox;
+    static long long server_linger_us() {
+        static const long long us = [] {
+            const char *v = getenv("SPCIES_CUDA_SERVER_LINGER_US");    // 0: no server, every single-instance call is a launch
+            return v ? atoll(v) : 200LL;
+        }();
+        return us;
+    }
+    // tell a running server to exit (it also exits by itself once idle for the linger time); wait = until it has
+    static void stop_server(DeviceCtx &c, bool wait) {
+        if (!c.h_mb) return;
+        Mailbox *mb = static_cast<Mailbox *>(c.h_mb);
+        volatile unsigned int *alive = &mb->alive;
+        if (*alive) {
+            *reinterpret_cast<volatile unsigned int *>(&mb->in[0].cmd) = 1u;
+            if (wait) cudaStreamSynchronize(c.srv_stream);
+        }
+    }
+    int run_server(DeviceCtx &c, const Call &cl, Result &res) {
+        if (!c.h_mb) {
+            SPCIES_CK(cudaHostAlloc(&c.h_mb, sizeof(Mailbox), cudaHostAllocMapped));
+            memset(c.h_mb, 0, sizeof(Mailbox));
+            SPCIES_CK(cudaHostGetDevicePointer(&c.d_mb, c.h_mb, 0));
+            SPCIES_CK(cudaStreamCreateWithFlags(&c.srv_stream, cudaStreamNonBlocking));
+        }
+        Mailbox *mb = static_cast<Mailbox *>(c.h_mb);
+        volatile unsigned int *alive = &mb->alive, *cmd = &mb->in[0].cmd, *oseq = &mb->out.seq;
+        if (*cmd != 0) {                                 // a stop request is pending: let that server go first
+            if (*alive) SPCIES_CK(cudaStreamSynchronize(c.srv_stream));
+            *cmd = 0;
+        }
+        const unsigned int seq = ++c.srv_seq;
+        double pay[Mailbox::NL * 7] = {};
+        memcpy(pay, cl.x0, Traits::NN * 8);
+        memcpy(pay + Traits::NN, cl.xr, Traits::NN * 8);
+        memcpy(pay + 2 * Traits::NN, cl.ur, Traits::MM * 8);
+        const auto t0 = std::chrono::steady_clock::now();
+        for (int l = 0; l < Mailbox::NL; ++l)
+            for (int j = 0; j < 7; ++j) *reinterpret_cast<volatile double *>(&mb->in[l].v[j]) = pay[l * 7 + j];
+        std::atomic_thread_fence(std::memory_order_release);
+        for (int l = 0; l < Mailbox::NL; ++l) *reinterpret_cast<volatile unsigned int *>(&mb->in[l].seq) = seq;
+        std::atomic_thread_fence(std::memory_order_seq_cst);
+        int block = 0;
+        size_t smem = 0;
+        for (unsigned long long spin = 1;; ++spin) {
+            if (*oseq == seq) break;
+            if (!*alive) {                               // no server (never started, or it has just lingered out): start one
+                *alive = 1u;
+                std::atomic_thread_fence(std::memory_order_seq_cst);
+                const cudaError_t le = Traits::launch_server(c.srv_stream, c.d_consts, c.d_mb, seq - 1,
+                                                             (unsigned long long)server_linger_us() * 1000ULL, block, smem);
+                if (le != cudaSuccess) {
+                    *alive = 0u;
+                    SPCIES_CK(le);
+                }
+                res.launches += 1;
+            }
+            if ((spin & 0xfff) == 0 && std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() > 2000.0) {
+                cudaError_t e = cudaStreamQuery(c.srv_stream);
+                if (e != cudaSuccess && e != cudaErrorNotReady) SPCIES_CK(e);
+                return fail((int)cudaErrorLaunchTimeout, "the single-instance server did not answer");
+            }
+        }
+        std::atomic_thread_fence(std::memory_order_acquire);
+        res.kernel_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();     // request to answer
+        for (int j = 0; j < Traits::MM; ++j) cl.u[j] = *reinterpret_cast<volatile double *>(&mb->out.u[j]);
+        cl.k[0] = *reinterpret_cast<volatile int *>(&mb->out.k);
+        cl.e[0] = *reinterpret_cast<volatile int *>(&mb->out.e);
+        res.sum_k = cl.k[0];
+        res.n_nc = cl.e[0] < 0;
+        res.block = block; res.grid = 1; res.smem = (int)smem;
+        return 0;
+    }
+
     // Small host-buffer batches (the reference's single-instance call is a batch of one): latency is API calls, not bytes.
     // Inputs are memcpy'd into a pinned, device-mapped staging block that the kernel reads directly, results come back the same
     // way, the statistics are summed on the host: one memset, one launch, two event records and one synchronisation instead of
@@ -244,7 +329,7 @@ template <class Traits> struct Runtime {
     static constexpr long long SMALL_B = 64;
     static constexpr size_t stage_doubles() {
         return (size_t)SMALL_B * (2 * Traits::NN + 2 * Traits::MM + 1 + 2 * Traits::NMM + 1 + Traits::extra_width(0) + Traits::extra_width(1) +
-                                  Traits::extra_width(2) + Traits::extra_width(3));
+                                  Traits::extra_width(2) + Traits::extra_width(3) + 1);
     }
     int run_small(DeviceCtx &c, const Call &cl, Result &res) {
         const long long B = cl.B;
@@ -261,6 +346,7 @@ template <class Traits> struct Runtime {
         size_t o_ex[4];
         o_ex[0] = o_ke + SMALL_B;
         for (int i = 1; i < 4; ++i) o_ex[i] = o_ex[i - 1] + SMALL_B * Traits::extra_width(i - 1);
+        const size_t o_done = o_ex[3] + SMALL_B * Traits::extra_width(3);        // completion flags of the latency engine (one word per instance)
         memcpy(h + o_x0, cl.x0, (size_t)B * Traits::NN * 8);
         memcpy(h + o_xr, cl.xr, (size_t)B * Traits::NN * 8);
         memcpy(h + o_ur, cl.ur, (size_t)B * Traits::MM * 8);
@@ -282,6 +368,52 @@ template <class Traits> struct Runtime {
         io.k = reinterpret_cast<int *>(d + o_ke);
         io.e = io.k + SMALL_B;
         io.engine = cl.engine;
+        if (Traits::HAS_SERVER && B == 1 && !varb && cl.engine == SPCIES_CUDA_ENGINE_AUTO && server_linger_us() > 0 &&
+            Traits::single_engine(cl.arith, io))
+            return run_server(c, cl, res);
+        if (Traits::single_engine(cl.arith, io) && (!varb || Traits::HAS_VARB)) {
+            // latency engine: one CTA per instance; no queue, no events, and the host waits on per-instance completion flags the
+            // kernel sets in this (mapped) block after a system-wide fence -- a launch and a few PCIe round trips per call
+            volatile unsigned int *hd = reinterpret_cast<volatile unsigned int *>(h + o_done);
+            unsigned int seq = ++c.small_seq;
+            if (seq == 0) seq = ++c.small_seq;
+            io.done = reinterpret_cast<unsigned int *>(d + o_done);
+            io.done_seq = seq;
+            int block = 0;
+            size_t smem = 0;
+            const auto t0 = std::chrono::steady_clock::now();
+            SPCIES_CK(Traits::launch_single(varb, (int)B, c.stream, io, c.d_consts, block, smem, cl.x0, cl.xr, cl.ur));
+            bool done = false;
+            for (unsigned long long spin = 1; !done; ++spin) {
+                done = true;
+                for (long long i = 0; i < B; ++i)
+                    if (hd[i] != seq) {
+                        done = false;
+                        break;
+                    }
+                if (!done && (spin & 0xfff) == 0 &&
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() > 5.0)
+                    break;                                  // long solve (or a failed launch): wait the ordinary way
+            }
+            if (!done) {
+                SPCIES_CK(cudaStreamSynchronize(c.stream));
+                SPCIES_CK(cudaGetLastError());
+            }
+            std::atomic_thread_fence(std::memory_order_acquire);
+            res.kernel_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();   // launch to flag
+            memcpy(cl.u, h + o_u, (size_t)B * Traits::MM * 8);
+            const int *hk = reinterpret_cast<const int *>(h + o_ke), *he = hk + SMALL_B;
+            memcpy(cl.k, hk, (size_t)B * 4);
+            memcpy(cl.e, he, (size_t)B * 4);
+            for (long long i = 0; i < B; ++i) {
+                res.sum_k += hk[i];
+                res.n_nc += (he[i] < 0);
+            }
+            res.launches = 1;
+            res.block = block; res.grid = (int)B; res.smem = (int)smem;
+            return 0;
+        }
+        if (cl.engine == SPCIES_CUDA_ENGINE_SINGLE) return fail(SPCIES_CUDA_EUNSUPPORTED, "the latency engine (one CTA per instance) does not take this call");
         int block = cl.block > 0 ? cl.block : Traits::default_block(varb), ipb = 0;
         size_t smem = Traits::smem_bytes(block, varb);
         Traits::engine_shape(cl.arith, io, block, smem, ipb);
@@ -332,6 +464,7 @@ template <class Traits> struct Runtime {
         if (!cl.device_pointers && cl.sol == nullptr && B > 0 && B <= SMALL_B && cl.tail_mode != SPCIES_CUDA_TAIL_TWO_PHASE &&
             cl.tail_mode != SPCIES_CUDA_TAIL_CAPS)
             return run_small(c, cl, res);
+        stop_server(c, false);       // a lingering single-instance server gives its SM back (it would exit by itself a moment later)
         cudaStream_t s = (cl.device_pointers && cl.user_stream) ? cl.user_stream : c.stream;
         bool direct_out = false;
         BatchIO io;

@@ -143,6 +143,15 @@ template <class S> struct PolicyTraits {
     static void engine_shape(int, const BatchIO &, int &block, size_t &, int &ipb) { ipb = block; }
     static bool caps_engine(int, const BatchIO &) { return false; }
     static bool cl_engine(int, const BatchIO &) { return false; }     // no in-kernel closed loop: one launch per sampling time
+    static bool single_engine(int, const BatchIO &) { return false; } // no one-CTA-per-instance latency engine
+    static constexpr bool HAS_SERVER = false;                         // ... and no lingering server for the single-instance symbol
+    static cudaError_t launch_server(cudaStream_t, const void *, void *, unsigned int, unsigned long long, int &, size_t &) {
+        return cudaErrorNotSupported;
+    }
+    static cudaError_t launch_single(bool, int, cudaStream_t, const BatchIO &, const void *, int &, size_t &, const double *, const double *,
+                                     const double *) {
+        return cudaErrorNotSupported;
+    }
     static bool uses_scratch(int, const BatchIO &) { return true; }   // the global per-instance state of the scalar kernels
     static size_t engine_scratch_bytes(int, const BatchIO &, int) { return 0; }   // global scratch of a tensor-core engine, if any
     static constexpr int K_MAX = 0;

@@ -37,7 +37,7 @@ class BatchInfo(ctypes.Structure):
 
 ARITH_FAST, ARITH_EXACT = 0, 1
 TAIL_AUTO, TAIL_SINGLE, TAIL_TWO_PHASE, TAIL_CAPS = 0, 1, 2, 3
-ENGINE_AUTO, ENGINE_SCALAR, ENGINE_MMA = 0, 1, 2
+ENGINE_AUTO, ENGINE_SCALAR, ENGINE_MMA, ENGINE_SINGLE = 0, 1, 2, 3
 
 
 class SpciesCudaError(RuntimeError):

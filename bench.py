@@ -637,8 +637,10 @@ def main():
                 c_p50 = None
         single = {'p50_us': c_p50 if c_p50 is not None else g50, 'p50_us_ctypes': g50, 'p99_us_ctypes': g99, 'k': int(ks),
                   'cpu_reference_us': c_us,
-                  'how': 'single-instance symbol (batch of one: H2D, kernel, D2H): p50 of 200 calls from plain C (harness/main_batch) when '
-                         'available, p50 / p99 of 1000 calls through ctypes; reference C solver: mean of %d identical solves, one thread' % nrep}
+                  'how': 'single-instance symbol: p50 of 200 back-to-back calls from plain C (harness/main_batch) when available, p50 / p99 '
+                         'of 1000 calls through ctypes; FISTA solvers: served by the lingering one-CTA kernel through its mapped-memory '
+                         'mailbox (SPCIES_CUDA_SERVER_LINGER_US, default 200; 0 = one launch per call), others: a batch of one; '
+                         'reference C solver: mean of %d identical solves, one thread' % nrep}
 
     # ---- closed loop on the device: `steps` sampling times of u = MPC(x), x+ = A x + B u for every instance
     closed = None

@@ -19,6 +19,7 @@
 #pragma once
 #include "spcies_kernel.cuh"
 #include "spcies_mma.cuh"
+#include "spcies_dense_mma.cuh"
 
 namespace spcies {
 namespace admm {
@@ -442,42 +443,83 @@ struct Solver {
 };
 
 #include "MPC_ADMM_mma.cuh"
+#include "MPC_ADMM_dense.cuh"
 
-// Host-side traits: the scalar skeleton plus the tensor-core engine (equMPC, FAST arithmetic, no debug payload)
+// Host-side traits: the scalar skeleton plus the tensor-core engines (FAST arithmetic, no debug payload): the banded one
+// (MPC_ADMM_mma.cuh) for the systems it takes, else the generic dense one (MPC_ADMM_dense.cuh: equMPC / laxMPC, any size,
+// vector rho, VAR_BOUNDS)
 struct Traits : PolicyTraits<Solver> {
     typedef PolicyTraits<Solver> Base;
-#if SPCIES_ADMM_MMA_ELIGIBLE
     static bool &mma_ok() {
         static bool ok = false;   // set by fill_blob(): the generated constants are uniform over the horizon
         return ok;
     }
-    static size_t blob_bytes() { return HAS_MMA ? MMA_OFFSET + MMA_BYTES : Base::blob_bytes(); }
+#if SPCIES_TERMINAL != 2
+    typedef dense::Plan<DenseEngine> DP;
+#endif
+    static size_t blob_bytes() {
+#if SPCIES_TERMINAL != 2
+        if (HAS_DENSE) return DP::BLOB_BYTES;
+#endif
+#if SPCIES_ADMM_MMA_ELIGIBLE
+        if (HAS_MMA) return MMA_OFFSET + MMA_BYTES;
+#endif
+        return Base::blob_bytes();
+    }
     static void fill_blob(void *dst) {
         memset(dst, 0, blob_bytes());
         Base::fill_blob(dst);
+#if SPCIES_ADMM_MMA_ELIGIBLE
         if constexpr (HAS_MMA) {
             MmaTables *T = new MmaTables;
             mma_ok() = fill_mma_tables(spcies_h_consts, *T);
             memcpy((char *)dst + MMA_OFFSET, T, sizeof *T);
             delete T;
         }
+#endif
+#if SPCIES_TERMINAL != 2
+        if constexpr (HAS_DENSE) {
+            DenseEngine::Small *S = new DenseEngine::Small;
+            memset(S, 0, sizeof *S);
+            long double *F = new long double[(size_t)DenseEngine::NO * 8 * DP::NIN * 8]();
+            DenseEngine::fill(spcies_h_consts, *S, F);
+            dense::fill_fragments<DenseEngine>(F, reinterpret_cast<double2 *>((char *)dst + DP::OFF_FRAG));
+            memcpy((char *)dst + DP::OFF_SMALL, S, sizeof *S);
+            delete[] F;
+            delete S;
+        }
+#endif
     }
     static bool use_mma(int arith, const BatchIO &io) {
         if constexpr (!HAS_MMA) return false;
         return mma_ok() && arith != SPCIES_CUDA_ARITH_EXACT && io.sol == nullptr && io.engine != SPCIES_CUDA_ENGINE_SCALAR;
     }
-    static bool uses_scratch(int arith, const BatchIO &io) { return !use_mma(arith, io); }
+    static bool use_dense(int arith, const BatchIO &io) {
+        if constexpr (!HAS_DENSE) return false;
+        return arith != SPCIES_CUDA_ARITH_EXACT && io.sol == nullptr && io.engine != SPCIES_CUDA_ENGINE_SCALAR && io.LB == nullptr;
+    }
+    static bool uses_scratch(int arith, const BatchIO &io) { return !use_mma(arith, io) && !use_dense(arith, io); }
     static void engine_shape(int arith, const BatchIO &io, int &block, size_t &smem, int &ipb) {
         ipb = block;
+#if SPCIES_ADMM_MMA_ELIGIBLE
         if (use_mma(arith, io)) {
             block = MMA_BLOCK;
             smem = MMA_SMEM;
             ipb = MMA_IPB;
         }
+#endif
+#if SPCIES_TERMINAL != 2
+        if (use_dense(arith, io)) {
+            block = DP::BLOCK;
+            smem = DP::SMEM;
+            ipb = DP::IPB;
+        }
+#endif
     }
     static cudaError_t launch(int arith, bool varb, int grid, int block, size_t smem, cudaStream_t s, const BatchIO &io,
                               const void *dc, void *scratch) {
-        if (io.engine == SPCIES_CUDA_ENGINE_MMA && !use_mma(arith, io)) return cudaErrorNotSupported;
+        if (io.engine == SPCIES_CUDA_ENGINE_MMA && !use_mma(arith, io) && !use_dense(arith, io)) return cudaErrorNotSupported;
+#if SPCIES_ADMM_MMA_ELIGIBLE
         if constexpr (HAS_MMA) {
             if (use_mma(arith, io)) {
                 auto kern = varb ? admm_mma_kernel<true> : admm_mma_kernel<false>;
@@ -487,18 +529,35 @@ struct Traits : PolicyTraits<Solver> {
                 return cudaGetLastError();
             }
         }
+#endif
+#if SPCIES_TERMINAL != 2
+        if constexpr (HAS_DENSE) {
+            if (use_dense(arith, io)) {
+                cudaError_t e = cudaFuncSetAttribute(dense::dense_mma_kernel<DenseEngine>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DP::SMEM);
+                if (e != cudaSuccess) return e;
+                dense::dense_mma_kernel<DenseEngine><<<grid, DP::BLOCK, DP::SMEM, s>>>(io, (const unsigned char *)dc);
+                return cudaGetLastError();
+            }
+        }
+#endif
         BatchIO io2 = io;
         io2.engine = SPCIES_CUDA_ENGINE_AUTO;
         return Base::launch(arith, varb, grid, block, smem, s, io2, dc, scratch);
     }
     static cudaError_t attributes(int arith, bool varb, cudaFuncAttributes *a) {
+#if SPCIES_ADMM_MMA_ELIGIBLE
         if constexpr (HAS_MMA) {
             if (mma_ok() && arith != SPCIES_CUDA_ARITH_EXACT)
                 return varb ? cudaFuncGetAttributes(a, admm_mma_kernel<true>) : cudaFuncGetAttributes(a, admm_mma_kernel<false>);
         }
+#endif
+#if SPCIES_TERMINAL != 2
+        if constexpr (HAS_DENSE) {
+            if (arith != SPCIES_CUDA_ARITH_EXACT && !varb) return cudaFuncGetAttributes(a, dense::dense_mma_kernel<DenseEngine>);
+        }
+#endif
         return Base::attributes(arith, varb, a);
     }
-#endif
 };
 
 }  // namespace admm

@@ -59,6 +59,7 @@
 #include "spcies_host.cuh"
 #include "spcies_tmem.cuh"
 #include "spcies_mma.cuh"
+#include "spcies_dense_mma.cuh"
 
 // Compile-time switches (set by the generator / tools/variants.py)
 #ifndef SPCIES_FISTA_TMEM
@@ -708,6 +709,7 @@ __global__ void __launch_bounds__(BLOCK, 1) fista_kernel(const BatchIO io, const
 
 #include "MPC_FISTA_mma.cuh"
 #include "MPC_FISTA_single.cuh"
+#include "MPC_FISTA_dense.cuh"
 
 struct Traits {
     static constexpr int NN = n, MM = m, NMM = nm;
@@ -723,7 +725,11 @@ struct Traits {
     typedef spcies_consts Consts;
     static const Consts &host_consts() { return spcies_h_consts; }
     // device constant blob: the generated constants + the derived FAST-mode blocks
-    static size_t blob_bytes() { return (HAS_MMA ? TOTAL_BLOB_BYTES : BLOB_BYTES) + (HAS_SINGLE ? SINGLE_BYTES : 0); }
+    typedef dense::Plan<DenseEngine> DP;
+    static size_t blob_bytes() {
+        if (HAS_DENSE) return DP::BLOB_BYTES;
+        return (HAS_MMA ? TOTAL_BLOB_BYTES : BLOB_BYTES) + (HAS_SINGLE ? SINGLE_BYTES : 0);
+    }
     static void fill_blob(void *dst) {
         memset(dst, 0, blob_bytes());
         memcpy(dst, &spcies_h_consts, sizeof spcies_h_consts);
@@ -737,11 +743,25 @@ struct Traits {
             delete T;
         }
         delete D;
-        if constexpr (HAS_SINGLE) {
-            SingleTables *S = new SingleTables;
-            fill_single_tables(spcies_h_consts, *S);
-            memcpy((char *)dst + SINGLE_OFFSET, S, sizeof *S);
-            delete S;
+        if constexpr (HAS_SINGLE || HAS_DENSE) {
+            PrimalForm *PF = new PrimalForm(spcies_h_consts);
+            if constexpr (HAS_SINGLE) {
+                SingleTables *S = new SingleTables;
+                fill_single_tables(*PF, *S);
+                memcpy((char *)dst + SINGLE_OFFSET, S, sizeof *S);
+                delete S;
+            }
+            if constexpr (HAS_DENSE) {
+                DenseEngine::Small *S = new DenseEngine::Small;
+                memset(S, 0, sizeof *S);
+                long double *F = new long double[(size_t)DenseEngine::NO * 8 * DP::NIN * 8]();
+                DenseEngine::fill(*PF, *S, F);
+                dense::fill_fragments<DenseEngine>(F, reinterpret_cast<double2 *>((char *)dst + DP::OFF_FRAG));
+                memcpy((char *)dst + DP::OFF_SMALL, S, sizeof *S);
+                delete[] F;
+                delete S;
+            }
+            delete PF;
         }
     }
     // latency engine (one CTA per instance) for small host-buffer calls: FAST arithmetic, no debug payload
@@ -787,6 +807,13 @@ struct Traits {
         if constexpr (!HAS_MMA) return false;
         return arith != SPCIES_CUDA_ARITH_EXACT && io.sol == nullptr && io.engine != SPCIES_CUDA_ENGINE_SCALAR;
     }
+    // systems the banded engine does not take (nn_ + mm_ > 8, N > 12): the generic dense tensor-core engine (MPC_FISTA_dense.cuh)
+    static bool use_dense(int arith, const BatchIO &io) {
+        if constexpr (!HAS_DENSE) return false;
+        return arith != SPCIES_CUDA_ARITH_EXACT && io.sol == nullptr && io.LB == nullptr &&
+               (io.engine == SPCIES_CUDA_ENGINE_AUTO || io.engine == SPCIES_CUDA_ENGINE_MMA);
+    }
+    static bool park_engine(int arith, const BatchIO &io) { return !use_dense(arith, io); }   // park & resume: the FISTA kernels of this file
     static bool caps_engine(int arith, const BatchIO &io) { return use_mma(arith, io); }   // iteration-cap rounds
     static bool cl_engine(int arith, const BatchIO &io) { return use_mma(arith, io) && io.LB == nullptr; }   // closed loop inside the kernel
     static void engine_shape(int arith, const BatchIO &io, int &block, size_t &smem, int &ipb) {
@@ -795,6 +822,10 @@ struct Traits {
             block = (io.phase != 2 && io.B >= MMA_BULK_MIN) ? MMA_BLOCK_BULK : MMA_BLOCK;
             smem = MMA_BYTES;
             ipb = block / 4;
+        } else if (use_dense(arith, io)) {
+            block = DP::BLOCK;
+            smem = DP::SMEM;
+            ipb = DP::IPB;
         }
     }
     static cudaError_t init_device_symbols() {
@@ -837,8 +868,17 @@ struct Traits {
     static cudaError_t launch(int arith, bool varb, int grid, int block, size_t smem, cudaStream_t s, const BatchIO &io,
                               const void *dc, void *) {
         const bool ex = arith == SPCIES_CUDA_ARITH_EXACT;
-        if (io.engine == SPCIES_CUDA_ENGINE_MMA && !use_mma(arith, io)) return cudaErrorNotSupported;
+        if (io.engine == SPCIES_CUDA_ENGINE_MMA && !use_mma(arith, io) && !use_dense(arith, io)) return cudaErrorNotSupported;
         if (io.engine == SPCIES_CUDA_ENGINE_SINGLE) return cudaErrorNotSupported;      // only through launch_single (small host-buffer calls)
+        if constexpr (HAS_DENSE) {
+            if (use_dense(arith, io)) {
+                if (io.cl_steps > 0) return cudaErrorNotSupported;
+                cudaError_t e = cudaFuncSetAttribute(dense::dense_mma_kernel<DenseEngine>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DP::SMEM);
+                if (e != cudaSuccess) return e;
+                dense::dense_mma_kernel<DenseEngine><<<grid, DP::BLOCK, DP::SMEM, s>>>(io, (const unsigned char *)dc);
+                return cudaGetLastError();
+            }
+        }
         if constexpr (HAS_MMA) {
             if (use_mma(arith, io)) {
                 const bool bulk = block == MMA_BLOCK_BULK && MMA_BLOCK_BULK != MMA_BLOCK;
@@ -863,6 +903,9 @@ struct Traits {
         const bool ex = arith == SPCIES_CUDA_ARITH_EXACT;
         if constexpr (HAS_MMA) {
             if (!ex) return varb ? cudaFuncGetAttributes(a, fista_mma_kernel<true, MMA_BLOCK, false>) : cudaFuncGetAttributes(a, fista_mma_kernel<false, MMA_BLOCK, false>);
+        }
+        if constexpr (HAS_DENSE) {
+            if (!ex && !varb) return cudaFuncGetAttributes(a, dense::dense_mma_kernel<DenseEngine>);
         }
         if (varb)
             return ex ? cudaFuncGetAttributes(a, fista_kernel<true, true, BLOCK1_VARB, USE_TMEM>)

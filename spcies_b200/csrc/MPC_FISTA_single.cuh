@@ -56,136 +56,170 @@ constexpr size_t SINGLE_BYTES = (sizeof(SingleTables) + 15) / 16 * 16;
 constexpr size_t SINGLE_OFFSET = HAS_MMA ? TOTAL_BLOB_BYTES : BLOB_BYTES;
 constexpr size_t SINGLE_SMEM = (size_t)(2 * SG_ZPAD + 2 * nm) * sizeof(double) + 16;
 
-#if SPCIES_FISTA_SINGLE
-static inline void fill_single_tables(const spcies_consts &C, SingleTables &T) {
+// ---- the iteration in the space of the primal variable, as dense host-side matrices (extended precision) -------------------------
+// Shared by the latency engine below and by the dense tensor-core policy (MPC_FISTA_dense.cuh).
+struct PrimalForm {
     typedef long double ld;
-    memset(&T, 0, sizeof T);
+    static constexpr int ROWS = SG_ROWS, ZLEN = SG_ZLEN;
+    ld *E, *P, *G0, *G1;            // E [ROWS][ZLEN]; P = E' W^-1 E [ZLEN][ZLEN]; g = G0 x0 + G1 xr, [ZLEN][n] each (G1 = 0 for laxMPC)
+    ld (*bA)[n];                    // b = bA x0 [+ xr in the last block for equMPC], [ROWS][n]
+    double Hd[ZLEN], cq[ZLEN], LB[ZLEN], UB[ZLEN];     // z_e = clip(Hd_e (q_e + v_e)), q_e = cq_e ref[qsrc_e], ref = (xr, ur)
+    int qsrc[ZLEN], comp[ZLEN];     // comp: the component of (x, u) a primal variable is (per-instance bounds)
+    double beta[SG_KTAB];           // momentum coefficient (t_{k-1} - 1) / t_k of iteration k   (:374-381)
     // primal variable e: u_0[j] | z[l][j] (x_{l+1}, u_{l+1}) | z_N[j]
-    auto el_u0 = [](int j) { return j; };
-    auto el_z = [](int l, int j) { return m + l * nm + j; };
-    auto el_zN = [](int j) { return m + (N - 1) * nm + j; };
+    static int el_u0(int j) { return j; }
+    static int el_z(int l, int j) { return m + l * nm + j; }
+    static int el_zN(int j) { return m + (N - 1) * nm + j; }
+    void primal(int e, double hd, double cq_, int src, int cmp, double lb, double ub) {
+        Hd[e] = hd;
+        cq[e] = cq_;
+        qsrc[e] = src;
+        comp[e] = cmp;
+        LB[e] = lb;
+        UB[e] = ub;
+    }
+    explicit PrimalForm(const spcies_consts &C) {
+        for (int j = 0; j < m; ++j)                                               // :478-495
+#ifdef VAR_BOUNDS
+            primal(el_u0(j), (double)C.QRi[n + j], (double)C.R[j], n + j, n + j, (double)C.LB0[j], (double)C.UB0[j]);
+#else
+            primal(el_u0(j), (double)C.QRi[n + j], (double)C.R[j], n + j, n + j, (double)C.LB[n + j], (double)C.UB[n + j]);
+#endif
+        for (int l = 0; l < N - 1; ++l)                                           // :498-521
+            for (int j = 0; j < nm; ++j)
+#ifdef VAR_BOUNDS
+                primal(el_z(l, j), (double)C.QRi[j], j < n ? (double)C.Q[j] : (double)C.R[j - n], j, j, (double)C.LB[l][j], (double)C.UB[l][j]);
+#else
+                primal(el_z(l, j), (double)C.QRi[j], j < n ? (double)C.Q[j] : (double)C.R[j - n], j, j, (double)C.LB[j], (double)C.UB[j]);
+#endif
+#if SPCIES_TERMINAL
+        for (int j = 0; j < n; ++j)                                               // :524-537
+#ifdef VAR_BOUNDS
+            primal(el_zN(j), (double)C.Ti[j], (double)C.T[j], j, j, (double)C.LBN[j], (double)C.UBN[j]);
+#else
+            primal(el_zN(j), (double)C.Ti[j], (double)C.T[j], j, j, (double)C.LB[j], (double)C.UB[j]);
+#endif
+#endif
+        // E (rows of the residual, :546-574) as a dense matrix; b = -A x0 (:275-280)
+        E = new ld[(size_t)ROWS * ZLEN]();
+        bA = new ld[ROWS][n]();
+        for (int l = 0; l < N; ++l)
+            for (int j = 0; j < n; ++j) {
+                ld *row = E + (size_t)(l * n + j) * ZLEN;
+                if (l == 0) {
+                    for (int c = 0; c < m; ++c) row[el_u0(c)] = -(ld)C.AB[j][n + c];
+                    for (int c = 0; c < n; ++c) bA[j][c] = -(ld)C.AB[j][c];
+                } else {
+                    for (int c = 0; c < nm; ++c) row[el_z(l - 1, c)] = -(ld)C.AB[j][c];
+                }
+                if (l < N - 1) row[el_z(l, j)] = 1;
+                else if (TERMINAL) row[el_zN(j)] = 1;
+            }
+        // W^-1: the reference's solve (forward / backward substitution with Alpha, Beta) applied to the unit vectors   :577-651
+        ld *Wi = new ld[(size_t)ROWS * ROWS]();
+        for (int c = 0; c < ROWS; ++c) {
+            ld mu[N][n] = {};
+            mu[c / n][c % n] = 1;
+            for (int l = 0; l < N; ++l)                                            // forward substitution
+                for (int j = 0; j < n; ++j) {
+                    if (l > 0)
+                        for (int i = 0; i < n; ++i) mu[l][j] -= (ld)C.Alpha[l - 1][i][j] * mu[l - 1][i];
+                    for (int i = 0; i < j; ++i) mu[l][j] -= (ld)C.Beta[l][i][j] * mu[l][i];
+                    mu[l][j] *= (ld)C.Beta[l][j][j];
+                }
+            for (int l = N - 1; l >= 0; --l)                                       // backward substitution
+                for (int j = n - 1; j >= 0; --j) {
+                    if (l < N - 1)
+                        for (int i = 0; i < n; ++i) mu[l][j] -= (ld)C.Alpha[l][j][i] * mu[l + 1][i];
+                    for (int i = n - 1; i > j; --i) mu[l][j] -= (ld)C.Beta[l][j][i] * mu[l][i];
+                    mu[l][j] *= (ld)C.Beta[l][j][j];
+                }
+            for (int r = 0; r < ROWS; ++r) Wi[(size_t)r * ROWS + c] = mu[r / n][r % n];
+        }
+        ld *M = new ld[(size_t)ROWS * ZLEN]();                                     // W^-1 E
+        for (int i = 0; i < ROWS; ++i)
+            for (int c = 0; c < ZLEN; ++c) {
+                ld v = 0;
+                for (int r = 0; r < ROWS; ++r) v += Wi[(size_t)i * ROWS + r] * E[(size_t)r * ZLEN + c];
+                M[(size_t)i * ZLEN + c] = v;
+            }
+        P = new ld[(size_t)ZLEN * ZLEN]();
+        G0 = new ld[(size_t)ZLEN * n]();
+        G1 = new ld[(size_t)ZLEN * n]();
+        for (int e = 0; e < ZLEN; ++e) {
+            for (int c = 0; c < n; ++c) {                                          // g = E' W^-1 b, b = bA x0 [+ xr in the last block]
+                ld v0 = 0, v1 = 0;
+                for (int i = 0; i < ROWS; ++i) {
+                    ld wb = 0;
+                    for (int r = 0; r < n; ++r) wb += Wi[(size_t)i * ROWS + r] * bA[r][c];
+                    v0 += E[(size_t)i * ZLEN + e] * wb;
+                    if (!TERMINAL) v1 += E[(size_t)i * ZLEN + e] * Wi[(size_t)i * ROWS + (N - 1) * n + c];
+                }
+                G0[(size_t)e * n + c] = v0;
+                G1[(size_t)e * n + c] = v1;
+            }
+            for (int col = 0; col < ZLEN; ++col) {
+                ld v = 0;
+                for (int i = 0; i < ROWS; ++i) v += E[(size_t)i * ZLEN + e] * M[(size_t)i * ZLEN + col];
+                P[(size_t)e * ZLEN + col] = v;
+            }
+        }
+        delete[] M;
+        delete[] Wi;
+        // momentum coefficients: t_0 = 1, t_k = (1 + sqrt(1 + 4 t_{k-1}^2)) / 2, beta_k = (t_{k-1} - 1) / t_k, in double like the reference
+        double t = 1.0;
+        beta[0] = 0.0;
+        for (int k = 1; k < SG_KTAB; ++k) {
+            const double t1 = t;
+            t = 0.5 * (1.0 + sqrt(1.0 + 4.0 * t1 * t1));
+            beta[k] = (t1 - 1.0) / t;
+        }
+    }
+    ~PrimalForm() {
+        delete[] E;
+        delete[] P;
+        delete[] G0;
+        delete[] G1;
+        delete[] bA;
+    }
+    PrimalForm(const PrimalForm &) = delete;
+    PrimalForm &operator=(const PrimalForm &) = delete;
+};
+
+#if SPCIES_FISTA_SINGLE
+static inline void fill_single_tables(const PrimalForm &F, SingleTables &T) {
+    memset(&T, 0, sizeof T);
     for (int t = 0; t < SG_MR; ++t) {
         T.LB[t] = -1e300;
         T.UB[t] = 1e300;
-        T.comp[t] = T.qsrc[t] = 0;
     }
     for (int t = 0; t < SG_RR; ++t) T.bx[t] = -1;
-    auto primal = [&](int e, double hd, double cq, int src, int comp, double lb, double ub) {
-        const int t = e;
-        T.Hd[t] = hd;
-        T.cq[t] = cq;
-        T.qsrc[t] = src;
-        T.comp[t] = comp;
-        T.LB[t] = lb;
-        T.UB[t] = ub;
-    };
-    for (int j = 0; j < m; ++j)                                               // :478-495
-#ifdef VAR_BOUNDS
-        primal(el_u0(j), (double)C.QRi[n + j], (double)C.R[j], n + j, n + j, (double)C.LB0[j], (double)C.UB0[j]);
-#else
-        primal(el_u0(j), (double)C.QRi[n + j], (double)C.R[j], n + j, n + j, (double)C.LB[n + j], (double)C.UB[n + j]);
-#endif
-    for (int l = 0; l < N - 1; ++l)                                           // :498-521
-        for (int j = 0; j < nm; ++j)
-#ifdef VAR_BOUNDS
-            primal(el_z(l, j), (double)C.QRi[j], j < n ? (double)C.Q[j] : (double)C.R[j - n], j, j, (double)C.LB[l][j], (double)C.UB[l][j]);
-#else
-            primal(el_z(l, j), (double)C.QRi[j], j < n ? (double)C.Q[j] : (double)C.R[j - n], j, j, (double)C.LB[j], (double)C.UB[j]);
-#endif
-#if SPCIES_TERMINAL
-    for (int j = 0; j < n; ++j)                                               // :524-537
-#ifdef VAR_BOUNDS
-        primal(el_zN(j), (double)C.Ti[j], (double)C.T[j], j, j, (double)C.LBN[j], (double)C.UBN[j]);
-#else
-        primal(el_zN(j), (double)C.Ti[j], (double)C.T[j], j, j, (double)C.LB[j], (double)C.UB[j]);
-#endif
-#endif
-    // E (rows of the residual, :546-574) as a dense matrix; b = -A x0 (:275-280)
-    ld *E = new ld[(size_t)SG_ROWS * SG_ZLEN]();
-    ld(*bA)[n] = new ld[SG_ROWS][n]();          // b_i = sum_j bA[i][j] x0_j
-    for (int l = 0; l < N; ++l)
-        for (int j = 0; j < n; ++j) {
-            ld *row = E + (size_t)(l * n + j) * SG_ZLEN;
-            if (l == 0) {
-                for (int c = 0; c < m; ++c) row[el_u0(c)] = -(ld)C.AB[j][n + c];
-                for (int c = 0; c < n; ++c) bA[j][c] = -(ld)C.AB[j][c];
-            } else {
-                for (int c = 0; c < nm; ++c) row[el_z(l - 1, c)] = -(ld)C.AB[j][c];
-            }
-            if (l < N - 1) row[el_z(l, j)] = 1;
-            else if (TERMINAL) row[el_zN(j)] = 1;
+    for (int e = 0; e < SG_ZLEN; ++e) {
+        T.Hd[e] = F.Hd[e];
+        T.cq[e] = F.cq[e];
+        T.qsrc[e] = F.qsrc[e];
+        T.comp[e] = F.comp[e];
+        T.LB[e] = F.LB[e];
+        T.UB[e] = F.UB[e];
+        for (int c = 0; c < n; ++c) {
+            T.cg[c][e] = (double)F.G0[(size_t)e * n + c];
+            T.cg[n + c][e] = (double)F.G1[(size_t)e * n + c];
         }
-    // W^-1: the reference's solve (forward / backward substitution with Alpha, Beta) applied to the unit vectors   :577-651
-    ld *Wi = new ld[(size_t)SG_ROWS * SG_ROWS]();
-    for (int c = 0; c < SG_ROWS; ++c) {
-        ld mu[N][n] = {};
-        mu[c / n][c % n] = 1;
-        for (int l = 0; l < N; ++l)                                            // forward substitution
-            for (int j = 0; j < n; ++j) {
-                if (l > 0)
-                    for (int i = 0; i < n; ++i) mu[l][j] -= (ld)C.Alpha[l - 1][i][j] * mu[l - 1][i];
-                for (int i = 0; i < j; ++i) mu[l][j] -= (ld)C.Beta[l][i][j] * mu[l][i];
-                mu[l][j] *= (ld)C.Beta[l][j][j];
-            }
-        for (int l = N - 1; l >= 0; --l)                                       // backward substitution
-            for (int j = n - 1; j >= 0; --j) {
-                if (l < N - 1)
-                    for (int i = 0; i < n; ++i) mu[l][j] -= (ld)C.Alpha[l][j][i] * mu[l + 1][i];
-                for (int i = n - 1; i > j; --i) mu[l][j] -= (ld)C.Beta[l][j][i] * mu[l][i];
-                mu[l][j] *= (ld)C.Beta[l][j][j];
-            }
-        for (int r = 0; r < SG_ROWS; ++r) Wi[(size_t)r * SG_ROWS + c] = mu[r / n][r % n];
+        for (int col = 0; col < SG_ZLEN; ++col) T.P[col][e] = (double)F.P[(size_t)e * SG_ZLEN + col];
     }
-    ld *M = new ld[(size_t)SG_ROWS * SG_ZLEN]();                               // W^-1 E
-    for (int i = 0; i < SG_ROWS; ++i)
-        for (int c = 0; c < SG_ZLEN; ++c) {
-            ld v = 0;
-            for (int r = 0; r < SG_ROWS; ++r) v += Wi[(size_t)i * SG_ROWS + r] * E[(size_t)r * SG_ZLEN + c];
-            M[(size_t)i * SG_ZLEN + c] = v;
-        }
     for (int i = 0; i < SG_ROWS; ++i) {
         int t = 0;
         for (int c = 0; c < SG_ZLEN; ++c) {
-            const ld v = E[(size_t)i * SG_ZLEN + c];
+            const long double v = F.E[(size_t)i * SG_ZLEN + c];
             if (v == 0) continue;
             T.c2[t][i] = (double)v;
             T.i2[t][i] = c;
             ++t;
         }
-        for (int c = 0; c < n; ++c) T.cb[c][i] = (double)bA[i][c];
+        for (int c = 0; c < n; ++c) T.cb[c][i] = (double)F.bA[i][c];
         if (!TERMINAL && i >= (N - 1) * n) T.bx[i] = i - (N - 1) * n;          // equMPC: x_N = xr   (code_equMPC_FISTA_C.c:549)
     }
-    for (int e = 0; e < SG_ZLEN; ++e) {
-        for (int c = 0; c < n; ++c) {                                          // g = E' W^-1 b, b = bA x0 [+ xr in the last block]
-            ld v0 = 0, v1 = 0;
-            for (int i = 0; i < SG_ROWS; ++i) {
-                ld wb = 0;
-                for (int r = 0; r < n; ++r) wb += Wi[(size_t)i * SG_ROWS + r] * bA[r][c];
-                v0 += E[(size_t)i * SG_ZLEN + e] * wb;
-                if (!TERMINAL) v1 += E[(size_t)i * SG_ZLEN + e] * Wi[(size_t)i * SG_ROWS + (N - 1) * n + c];
-            }
-            T.cg[c][e] = (double)v0;
-            T.cg[n + c][e] = (double)v1;
-        }
-        for (int col = 0; col < SG_ZLEN; ++col) {
-            ld v = 0;
-            for (int i = 0; i < SG_ROWS; ++i) v += E[(size_t)i * SG_ZLEN + e] * M[(size_t)i * SG_ZLEN + col];
-            T.P[col][e] = (double)v;
-        }
-    }
-    delete[] M;
-    {   // momentum coefficients: t_0 = 1, t_k = (1 + sqrt(1 + 4 t_{k-1}^2)) / 2, beta_k = (t_{k-1} - 1) / t_k, in double like the reference
-        double t = 1.0;
-        T.beta[0] = 0.0;
-        for (int k = 1; k < SG_KTAB; ++k) {
-            const double t1 = t;
-            t = 0.5 * (1.0 + sqrt(1.0 + 4.0 * t1 * t1));
-            T.beta[k] = (t1 - 1.0) / t;
-        }
-    }
-    delete[] Wi;
-    delete[] E;
-    delete[] bA;
+    memcpy(T.beta, F.beta, sizeof T.beta);
 }
 
 // ---- per-thread coefficients (registers), loaded once per kernel

@@ -33,6 +33,8 @@
 //              finish(Lane &, C, io, inst, st, t4)           write u_opt
 // Arithmetic: FAST only (explicit F, FMA, MMA accumulation order); EXACT, float and the debug payload use the scalar kernel.
 #pragma once
+#include <type_traits>
+#include <utility>
 #include "spcies_kernel.cuh"
 #include "spcies_mma.cuh"
 
@@ -41,6 +43,26 @@ namespace dense {
 
 constexpr size_t SMEM_LIMIT = 227 * 1024 - 256;
 constexpr int TILE_BYTES = 32 * sizeof(double2);   // 512
+
+// Optional members of an engine policy (detected):
+//   E::BLOB_OFFSET    position of (Small | fragments) in the device constant blob; default: right behind spcies_consts
+//   E::WARMUP         passes that come before the first counted iteration and have no exit test (FISTA: 1); default 0
+//   E::Lane::pass     if present, the engine keeps it equal to the index of the current pass of the instance (0, 1, ...) --
+//                     for policies whose step depends on the iteration number
+template <class E, class = void> struct BlobOffset {
+    static constexpr size_t value = (sizeof(spcies_consts) + 15) / 16 * 16;
+};
+template <class E> struct BlobOffset<E, std::void_t<decltype(E::BLOB_OFFSET)>> {
+    static constexpr size_t value = E::BLOB_OFFSET;
+};
+template <class E, class = void> struct Warmup {
+    static constexpr int value = 0;
+};
+template <class E> struct Warmup<E, std::void_t<decltype(E::WARMUP)>> {
+    static constexpr int value = E::WARMUP;
+};
+template <class L, class = void> struct HasPass : std::false_type {};
+template <class L> struct HasPass<L, std::void_t<decltype(std::declval<L &>().pass)>> : std::true_type {};
 
 template <class E> struct Plan {
     static constexpr int NB = E::NB;
@@ -73,8 +95,7 @@ template <class E> struct Plan {
     static constexpr int BLOCK = (CONSUMER_WARPS + 1) * 32;          // + the producer warp
     static constexpr int IPB = GROUPS * 8;
     static constexpr size_t SMEM = FIXED + RING_BYTES + (size_t)GROUPS * GROUP_BYTES;
-    static constexpr size_t CONSTS_BYTES_ = (sizeof(spcies_consts) + 15) / 16 * 16;
-    static constexpr size_t OFF_SMALL = CONSTS_BYTES_;               // blob: spcies_consts | Small | fragments
+    static constexpr size_t OFF_SMALL = BlobOffset<E>::value;        // blob: spcies_consts [| other tables] | Small | fragments
     static constexpr size_t OFF_FRAG = OFF_SMALL + SMALL_BYTES;
     static constexpr size_t BLOB_BYTES = OFF_FRAG + FRAG_BYTES;
     static constexpr bool HAS = E::OK && sizeof(SPCIES_REAL) == 8 && GROUPS >= 1 && NSTAGE <= 96;
@@ -261,13 +282,14 @@ template <class E> __global__ void __launch_bounds__(Plan<E>::BLOCK, 1) dense_mm
                 } else {
                     inst = slot;
                     E::init(L, C, S, io, inst, st, win + E::NW * 32, t4, rank);
-                    k = 0;
+                    k = -Warmup<E>::value;
                     live = true;
                 }
             }
             if (TEAM > 1) team_sync();      // the ranks of a team initialise different tiles
         }
         // ---- input vector w (tiles split over the team)
+        if constexpr (HasPass<typename E::Lane>::value) L.pass = k + Warmup<E>::value;
 #pragma unroll 1
         for (int t = rank; t < E::NW; t += TEAM) win[t * 32] = E::make_w(L, C, S, t, st, t4);
         team_sync();
@@ -353,7 +375,7 @@ template <class E> __global__ void __launch_bounds__(Plan<E>::BLOCK, 1) dense_mm
         if (live) k += 1;
         const bool gover = (ob & gmask) != 0u;
         if (live) {
-            const int ef = !gover ? 1 : ((k >= k_max) ? -1 : 0);
+            const int ef = (k >= 1 && !gover) ? 1 : ((k >= k_max) ? -1 : 0);      // (k < 1: a warm-up pass, no exit test)
             if (ef != 0) {
                 if (rank == 0) {
                     E::finish(L, C, io, inst, st, t4);

@@ -524,6 +524,7 @@ template <class Traits> struct Runtime {
             int mode = cl.tail_mode;
             if (mode == SPCIES_CUDA_TAIL_AUTO) mode = !big ? SPCIES_CUDA_TAIL_SINGLE : (caps_ok ? SPCIES_CUDA_TAIL_CAPS : SPCIES_CUDA_TAIL_TWO_PHASE);
             if (mode == SPCIES_CUDA_TAIL_CAPS && !caps_ok) mode = SPCIES_CUDA_TAIL_TWO_PHASE;
+            if (!Traits::park_engine(cl.arith, io)) mode = SPCIES_CUDA_TAIL_SINGLE;      // this call's engine cannot park instances
             two_phase = mode == SPCIES_CUDA_TAIL_TWO_PHASE;
             if (mode == SPCIES_CUDA_TAIL_CAPS) {
                 const int dflt[3] = {96, 320, 0};

@@ -106,3 +106,36 @@ def test_dense_engine_refused_where_it_cannot_run(name):
         sol.solve_batch(x0, xr, ur, arith=ARITH_EXACT, engine=ENGINE_MMA)
     with pytest.raises(SpciesCudaError):
         sol.solve_batch(x0, xr, ur, engine=ENGINE_MMA, want_sol=True)
+
+
+# ---- FISTA and ADMM solvers the banded engines do not take (other system sizes, penalty vectors, per-stage bounds): the generic
+#      dense engine instead of the one-thread-per-instance kernel (MPC_FISTA_dense.cuh, MPC_ADMM_dense.cuh)
+FALLBACK = ['S4_laxMPC_FISTA', 'S2_equMPC_ADMM', 'S4_equMPC_ADMM', 'S2_laxMPC_ADMM', 'S4_laxMPC_ADMM', 'T_equMPC_ADMM_vb',
+            'T_equMPC_ADMM_vrho']
+
+
+@pytest.mark.parametrize('name', FALLBACK)
+def test_dense_engine_takes_what_the_banded_engines_do_not(name):
+    sol, spec, cfg = prebuilt.get(name)
+    B = 1500
+    b = sysmodel.synthetic_batch(cfg['sys'], B, seed=66)
+    ur_, kr, er = _ref(name).solve_batch(b['x0'], b['xr'], b['ur'], threads=16)
+    u, k, e, info = sol.solve_batch(b['x0'], b['xr'], b['ur'], engine=ENGINE_MMA)            # an error if no tensor-core engine takes it
+    gate(spec, u, k, e, ur_, kr, er)
+    assert info['sum_k'] == int(k.sum()) and info['n_not_converged'] == int((e == -1).sum())
+    u2, k2, e2, info2 = sol.solve_batch(b['x0'], b['xr'], b['ur'])                           # ... and it is the default
+    assert np.array_equal(u2.view(np.uint64), u.view(np.uint64)) and np.array_equal(k2, k) and info2['block_threads'] == info['block_threads']
+    u3, k3, e3, info3 = sol.solve_batch(b['x0'][:256], b['xr'][:256], b['ur'][:256], engine=ENGINE_SCALAR)
+    gate(spec, u3, k3, e3, ur_[:256], kr[:256], er[:256])
+    ue, ke, ee, _ = sol.solve_batch(b['x0'][:256], b['xr'][:256], b['ur'][:256], arith=ARITH_EXACT)
+    assert np.array_equal(ue.view(np.uint64), ur_[:256].view(np.uint64)) and np.array_equal(ke, kr[:256]) and np.array_equal(ee, er[:256])
+
+
+@pytest.mark.parametrize('name', ['S4_laxMPC_FISTA', 'S4_equMPC_ADMM'])
+def test_dense_fallback_ragged_batches(name):
+    sol, spec, cfg = prebuilt.get(name)
+    for B in (65, 127, 129, 700):
+        b = sysmodel.synthetic_batch(cfg['sys'], B, seed=67)
+        ur_, kr, er = _ref(name).solve_batch(b['x0'], b['xr'], b['ur'], threads=8)
+        u, k, e, info = sol.solve_batch(b['x0'], b['xr'], b['ur'], engine=ENGINE_MMA)
+        gate(spec, u, k, e, ur_, kr, er)

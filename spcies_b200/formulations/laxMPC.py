@@ -247,6 +247,7 @@ def _cons_ADMM(recipe, terminal: bool) -> SolverSpec:
         defines=defs, constants=consts,
         ref_code=f'formulations/+{name}/code_{name}_ADMM_C.c',
         ref_header=f'formulations/+{name}/header_{name}_ADMM_C.h',
+        extra_inputs=('A_in', 'B_in', 'Q_in', 'R_in', 'LB_in', 'UB_in') if opts.time_varying else (),
         sol_fields=(('z', zlen), ('v', zlen), ('lambda', zlen)),
         vars=v, dims=dict(n=n, m=m, N=N))
 

@@ -652,9 +652,11 @@ def main():
             closed = {'instances': Bc, 'steps': steps, 'solver': spec.options.solver_key()}
             for label, kw in (('cold', dict(warm_start=0)), ('warm_shifted', dict(warm_start=2)), ('warm_unshifted', dict(warm_start=1))):
                 sol.closed_loop(bb['x0'][:4096], bb['xr'][:4096], bb['ur'][:4096], 2, want_x=False, **kw)
-                t0 = time.perf_counter()
-                _, _, kk, ee, ci = sol.closed_loop(bb['x0'], bb['xr'], bb['ur'], steps, want_x=False, **kw)
-                dt = time.perf_counter() - t0
+                dt = 1e30
+                for _rep in range(2):          # best of two: the first full-size call also grows the library's device buffers
+                    t0 = time.perf_counter()
+                    _, _, kk, ee, ci = sol.closed_loop(bb['x0'], bb['xr'], bb['ur'], steps, want_x=False, **kw)
+                    dt = min(dt, time.perf_counter() - t0)
                 closed[label] = {'mpc_steps_per_s': Bc * steps / dt, 'seconds': dt, 'device_ms': ci['kernel_ms'], 'launches': ci['launches'],
                                  'mean_k': ci['sum_k'] / (Bc * steps), 'n_not_converged': int(ci['n_not_converged'])}
             # the round-1 way: one host-buffer batched call per sampling time, plant step on the host

@@ -496,7 +496,8 @@ struct Traits : PolicyTraits<Solver> {
     }
     static bool use_dense(int arith, const BatchIO &io) {
         if constexpr (!HAS_DENSE) return false;
-        return arith != SPCIES_CUDA_ARITH_EXACT && io.sol == nullptr && io.engine != SPCIES_CUDA_ENGINE_SCALAR && io.LB == nullptr;
+        return arith != SPCIES_CUDA_ARITH_EXACT && io.sol == nullptr && io.LB == nullptr &&
+               (io.engine == SPCIES_CUDA_ENGINE_MMA || (io.engine == SPCIES_CUDA_ENGINE_AUTO && DENSE_PREFERRED));
     }
     static bool uses_scratch(int arith, const BatchIO &io) { return !use_mma(arith, io) && !use_dense(arith, io); }
     static void engine_shape(int arith, const BatchIO &io, int &block, size_t &smem, int &ipb) {

@@ -231,6 +231,11 @@ struct DenseEngine {
     }
 };
 constexpr bool HAS_DENSE = !HAS_MMA && dense::Plan<DenseEngine>::HAS;
+// AUTO picks it where it beats the one-thread-per-instance kernel: larger problems, and those whose iterates the scalar kernel
+// can only keep in its global scratch.  Measured on 64 Ki instances (tools/fallback_times.py, profiles/r2_fallback_times.json):
+// n = 8, m = 4, N = 8 (|z| = 88 / 96): 1.42x; n = 6, m = 2, N = 10 with a penalty vector (|z| = 74): 0.98x; n = 4, m = 2, N = 8 (|z| = 44): 0.66x
+constexpr bool DENSE_PREFERRED = HAS_DENSE && (DenseEngine::ZLEN >= 80 || KernelPlan<Solver>::GSTATE_FIXED);
 #else
 constexpr bool HAS_DENSE = false;
+constexpr bool DENSE_PREFERRED = false;
 #endif

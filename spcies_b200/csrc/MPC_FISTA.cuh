@@ -811,7 +811,7 @@ struct Traits {
     static bool use_dense(int arith, const BatchIO &io) {
         if constexpr (!HAS_DENSE) return false;
         return arith != SPCIES_CUDA_ARITH_EXACT && io.sol == nullptr && io.LB == nullptr &&
-               (io.engine == SPCIES_CUDA_ENGINE_AUTO || io.engine == SPCIES_CUDA_ENGINE_MMA);
+               (io.engine == SPCIES_CUDA_ENGINE_MMA || (io.engine == SPCIES_CUDA_ENGINE_AUTO && DENSE_PREFERRED));
     }
     static bool park_engine(int arith, const BatchIO &io) { return !use_dense(arith, io); }   // park & resume: the FISTA kernels of this file
     static bool caps_engine(int arith, const BatchIO &io) { return use_mma(arith, io); }   // iteration-cap rounds

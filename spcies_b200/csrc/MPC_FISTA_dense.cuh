@@ -136,3 +136,6 @@ struct DenseEngine {
     }
 };
 constexpr bool HAS_DENSE = !HAS_MMA && dense::Plan<DenseEngine>::HAS;
+// AUTO picks it where it beats the one-thread-per-instance kernel (measured: n = 8, m = 4, N = 8, |z| = 96: 1.30x on 64 Ki instances,
+// tools/fallback_times.py); smaller problems stay on the scalar kernel unless engine = SPCIES_CUDA_ENGINE_MMA asks for it
+constexpr bool DENSE_PREFERRED = HAS_DENSE && SG_ZLEN >= 80;

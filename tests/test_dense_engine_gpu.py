@@ -123,8 +123,10 @@ def test_dense_engine_takes_what_the_banded_engines_do_not(name):
     u, k, e, info = sol.solve_batch(b['x0'], b['xr'], b['ur'], engine=ENGINE_MMA)            # an error if no tensor-core engine takes it
     gate(spec, u, k, e, ur_, kr, er)
     assert info['sum_k'] == int(k.sum()) and info['n_not_converged'] == int((e == -1).sum())
-    u2, k2, e2, info2 = sol.solve_batch(b['x0'], b['xr'], b['ur'])                           # ... and it is the default
-    assert np.array_equal(u2.view(np.uint64), u.view(np.uint64)) and np.array_equal(k2, k) and info2['block_threads'] == info['block_threads']
+    u2, k2, e2, info2 = sol.solve_batch(b['x0'], b['xr'], b['ur'])       # the default: this engine where it is the faster one (|z| >= 80)
+    gate(spec, u2, k2, e2, ur_, kr, er)
+    if name.startswith('S4_'):
+        assert np.array_equal(u2.view(np.uint64), u.view(np.uint64)) and np.array_equal(k2, k) and info2['block_threads'] == info['block_threads']
     u3, k3, e3, info3 = sol.solve_batch(b['x0'][:256], b['xr'][:256], b['ur'][:256], engine=ENGINE_SCALAR)
     gate(spec, u3, k3, e3, ur_[:256], kr[:256], er[:256])
     ue, ke, ee, _ = sol.solve_batch(b['x0'][:256], b['xr'][:256], b['ur'][:256], arith=ARITH_EXACT)

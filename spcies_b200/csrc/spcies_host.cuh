@@ -790,6 +790,11 @@ template <class Traits> struct Runtime {
         if (B > 0 && steps > 0 && (!x0 || !xr || !ur || !u_traj || !k_traj || !e_traj || (Traits::HAS_R && !r)))
             return fail(SPCIES_CUDA_EINVAL, "NULL array argument");
         if (o.device_pointers || o.LB || o.UB) return fail(SPCIES_CUDA_EUNSUPPORTED, "closed loop: host arrays, generated bounds");
+#if defined(in_engineering) && in_engineering == 1
+        // the prediction model acts on scaled, incremental variables; the states of the simulation are in engineering units
+        if (o.plant_AB == nullptr)
+            return fail(SPCIES_CUDA_EUNSUPPORTED, "closed loop of an in_engineering solver: give the plant in engineering units (opts.plant_AB)");
+#endif
         if (o.arith != SPCIES_CUDA_ARITH_FAST && o.arith != SPCIES_CUDA_ARITH_EXACT) return fail(SPCIES_CUDA_EINVAL, "unknown arith mode");
         int ndev = o.n_devices > 1 ? o.n_devices : 1;
         int avail = device_count();

@@ -17,7 +17,7 @@ from . import sysmodel
 
 def _QR(sys):
     p = sys['p']
-    return sla.block_diag(15.0 * np.eye(p), np.eye(p)), 0.1 * np.eye(sys['m'])
+    return sla.block_diag(15.0 * np.eye(p), np.eye(sys['n'] - p)), 0.1 * np.eye(sys['m'])
 
 
 def _T_sumP(sys, Q, R):
@@ -26,8 +26,8 @@ def _T_sumP(sys, Q, R):
     return np.diag(P.sum(axis=1))
 
 
-def reference_test(name: str, N: int = 10, masses: int = 3, forces=None, **solver_overrides):
-    sys = sysmodel.oscillating_masses_sys(p=masses, F=forces)
+def reference_test(name: str, N: int = 10, masses: int = 3, forces=None, drop: int = 0, **solver_overrides):
+    sys = sysmodel.oscillating_masses_sys(p=masses, F=forces, drop=drop)
     Q, R = _QR(sys)
     st = sysmodel.tester_status(sys)
     if name in ('laxMPC_FISTA', 'laxMPC_ADMM'):

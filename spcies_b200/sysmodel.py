@@ -57,7 +57,7 @@ def dlqr(A, B, Q, R):
     return K, P
 
 
-def oscillating_masses_sys(Ts: float = 0.2, p: int = 3, F=None):
+def oscillating_masses_sys(Ts: float = 0.2, p: int = 3, F=None, drop: int = 0):
     """The 3-mass system of tests/spcies_tester.m:90-111 (== example_OscMass.m:17-36); ``p`` / ``F`` select another chain of
     +sp_utils/gen_oscillating_masses.m:28-59 (``p`` masses, forces on the masses flagged in ``F``; default: first and last),
     with the same masses / springs / bounds pattern -- the systems of other dimensions used by the shape tests.
@@ -70,11 +70,15 @@ def oscillating_masses_sys(Ts: float = 0.2, p: int = 3, F=None):
         F = [1, 0, 1] if p == 3 else [1] + [0] * (p - 2) + [1]
     Ac, Bc = gen_oscillating_masses(M, K, F)
     A, B = c2d_zoh(Ac, Bc, Ts)
+    if drop:
+        # an odd state dimension for the shape tests: the discrete model without its last `drop` velocity states (not a physical
+        # reduction -- just a linear system of that size with the same structure of bounds and weights)
+        A, B = A[:-drop, :-drop].copy(), B[:-drop].copy()
     n, m = B.shape
     sys = dict(
         A=A, B=B,
-        LBx=-np.concatenate([np.ones(p), 1000.0 * np.ones(p)]),
-        UBx=np.concatenate([0.3 * np.ones(p), 1000.0 * np.ones(p)]),
+        LBx=-np.concatenate([np.ones(p), 1000.0 * np.ones(p - drop)]),
+        UBx=np.concatenate([0.3 * np.ones(p), 1000.0 * np.ones(p - drop)]),
         LBu=-0.8 * np.ones(m),
         UBu=0.8 * np.ones(m),
         p=p, n=n, m=m,

@@ -169,12 +169,23 @@ def _fprintf(text):
     return ''.join(out)
 
 
+# Defects of the reference's HEADER templates that stop an option from compiling at all; the prototype is corrected in the
+# instantiated text (the .c template -- the algorithm -- is never touched):
+#   header_laxMPC_ADMM_C.h:25  the TIME_VARYING prototype names the solution type `solution` instead of sol_$INSERT_NAME$
+#                              (the definition in code_laxMPC_ADMM_C.c:19 has the right type)
+REF_HEADER_FIXUPS = {
+    'formulations/+laxMPC/header_laxMPC_ADMM_C.h': [('int *e_flag, solution *sol);', 'int *e_flag, sol_$INSERT_NAME$ *sol);')],
+}
+
+
 def construct(spec, save_name):
     """Return ``{'c': text, 'h': text}`` of the files the reference would write for platform 'C'."""
     files = {
         'c': _read('platforms/+C_code/generic_solver_struct.c').replace('$INSERT_SOLVER$', _read(spec.ref_code)),
         'h': _read(spec.ref_header),
     }
+    for old_, new_ in REF_HEADER_FIXUPS.get(spec.ref_header, ()):
+        files['h'] = files['h'].replace(old_, new_)
     for ext in files:
         t = _insert_snippets(files[ext], ext)
         t = t.replace('$INSERT_NAME$', save_name).replace('$INSERT_PATH$', '')

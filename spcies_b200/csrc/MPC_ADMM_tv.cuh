@@ -1,4 +1,4 @@
-// MPC_ADMM_tv.cuh -- batched equMPC ADMM solver with a *per-instance* model (options.time_varying, `#define TIME_VARYING 1`),
+// MPC_ADMM_tv.cuh -- batched equMPC (SPCIES_TERMINAL == 0) / laxMPC (== 1) ADMM solver with a *per-instance* model (options.time_varying, `#define TIME_VARYING 1`),
 // hand-written for sm_100a.  Every instance brings its own A, B (column-major, as MATLAB passes them), diagonal Q, R and bounds;
 // the factorisation the generator does off line for a fixed model runs on the device, once per instance:
 //
@@ -6,6 +6,8 @@
 //   block-Cholesky recursion of W = G H_hat^-1 G': Beta_0, Alpha_0, Beta_h = chol(A Qi A' + B Ri B' + Qi - Alpha_{h-1}' Alpha_{h-1})
 //   (diagonal stored inverted), Alpha_h = Beta_h^-T (-Qi A'), Beta_{N-1} without the Qi term          :155-255
 //   then the ADMM loop of the constant-model solver on that instance's Alpha / Beta / [A B] / Hi      :291-553
+// laxMPC (code_laxMPC_ADMM_C.c:108-633): the terminal state x_N with the dense Hi_N = T_rho_i = (T + rho I)^-1 (a generated
+// constant: T is not an argument), added to every entry of the last diagonal block before its factorisation.
 //
 // One thread owns one instance; its model, factor and iterates live in the per-instance state of the persistent skeleton
 // ([element][thread], coalesced, L2 resident).  Operation order is the reference's throughout, so Arith<EXACT> is bit-identical to
@@ -19,15 +21,17 @@
 #if defined(VAR_BOUNDS) || !defined(SCALAR_RHO)
 #error "TIME_VARYING needs fixed bounds along the horizon and a scalar rho (cons_equMPC_ADMM_C.m:46-51)"
 #endif
-#if SPCIES_TERMINAL != 0
-#error "MPC_ADMM_tv.cuh: the equMPC formulation only"
+#if SPCIES_TERMINAL != 0 && SPCIES_TERMINAL != 1
+#error "MPC_ADMM_tv.cuh: the equMPC and laxMPC formulations"
 #endif
 
 namespace spcies {
 namespace admm_tv {
 
 constexpr int n = nn_, m = mm_, nm = nm_, N = NN_;
-constexpr int ZLEN = m + (N - 1) * nm;
+constexpr bool LAX = SPCIES_TERMINAL == 1;
+constexpr int ZN = m + (N - 1) * nm;          // first element of the terminal state (laxMPC)
+constexpr int ZLEN = ZN + (LAX ? n : 0);
 
 struct Solver {
     typedef SPCIES_REAL real;
@@ -46,7 +50,7 @@ struct Solver {
     static constexpr int OFF_MU = OFF_V1 + ZLEN;                // [N][n]
     static constexpr int OFF_B = OFF_MU + N * n;                // [n]
     static constexpr int OFF_QV = OFF_B + n;                    // q [nm]
-    static constexpr int OFF_XR = OFF_QV + nm;                  // [n]
+    static constexpr int OFF_XR = OFF_QV + nm;                  // xr [n] (equMPC) | qT = T xr [n] (laxMPC)
     static constexpr int OFF_TMP = OFF_XR + n;                  // A Qi A' [n][n], B Ri B' [n][n] (factorisation only)
     static constexpr int STATE = OFF_TMP + 2 * n * n;
     static constexpr int STATE_VARB = STATE;
@@ -72,7 +76,7 @@ struct Solver {
 
         // Beta_h (upper triangular, diagonal inverted) from `base`(i, j) [- Alpha_{h-1}' Alpha_{h-1}]; Q_rho_i is added to the diagonal
         // before the square root except in the last block                                             :155-176, :190-216, :234-255
-        template <class Base> __device__ void beta_block(int h, bool with_alpha, bool with_qi, Base base) {
+        template <class Base> __device__ void beta_block(int h, bool with_alpha, bool with_qi, Base base, bool with_T = false) {
 #pragma unroll 1
             for (int i = 0; i < n; ++i)
 #pragma unroll 1
@@ -84,6 +88,9 @@ struct Solver {
                     }
 #pragma unroll 1
                     for (int l = 1; l <= i; ++l) v = A::nmsub(v, be(h, l - 1, i), be(h, l - 1, j));
+#if SPCIES_TERMINAL == 1
+                    if (with_T) v = A::add(v, (real)C->T_rho_i[i][j]);      // dense: added to every entry   code_laxMPC_ADMM_C.c:258
+#endif
                     if (i == j) {
                         if (with_qi) v = A::add(v, hi(i));
                         v = A::div(real(1), A::sqrt(v));
@@ -168,7 +175,7 @@ struct Solver {
                 beta_block(h, true, true, [&](int i, int j) { return A::add(s.ld(AQ + i * n + j), s.ld(BR + i * n + j)); });
                 alpha_block(h);
             }
-            beta_block(N - 1, true, false, [&](int i, int j) { return A::add(s.ld(AQ + i * n + j), s.ld(BR + i * n + j)); });
+            beta_block(N - 1, true, false, [&](int i, int j) { return A::add(s.ld(AQ + i * n + j), s.ld(BR + i * n + j)); }, LAX);
             // Q, R <- -Q, -R                                                                           :257-264
 #pragma unroll
             for (int i = 0; i < n; ++i) s.st(OFF_Q + i, -s.ld(OFF_Q + i));
@@ -182,7 +189,14 @@ struct Solver {
                 for (int i = 0; i < n; ++i) b = A::sub(b, A::mul(ab(j, i), x0[i]));
                 s.st(OFF_B + j, b);
                 s.st(OFF_QV + j, A::mul(s.ld(OFF_Q + j), xr[j]));
+#if SPCIES_TERMINAL == 1
+                real qT = real(0);                                                               // qT = T xr (T dense, negated)   :292-295
+#pragma unroll
+                for (int i = 0; i < n; ++i) qT = A::add(qT, A::mul((real)C->T[j][i], xr[i]));
+                s.st(OFF_XR + j, qT);
+#else
                 s.st(OFF_XR + j, xr[j]);
+#endif
             }
 #pragma unroll
             for (int j = 0; j < m; ++j) s.st(OFF_QV + n + j, A::mul(s.ld(OFF_R + j), ur[j]));
@@ -198,7 +212,7 @@ struct Solver {
             for (int e = 0; e < ZLEN; ++e) {
                 const real v = s.ld(OFF_V + e);
                 s.st(OFF_V1 + e, v);
-                const real q = e < m ? s.ld(OFF_QV + n + e) : s.ld(OFF_QV + (e - m) % nm);
+                const real q = e < m ? s.ld(OFF_QV + n + e) : (e < ZN ? s.ld(OFF_QV + (e - m) % nm) : s.ld(OFF_XR + e - ZN));
                 s.st(OFF_Z + e, A::sub(A::add(q, s.ld(OFF_LAM + e)), A::mul(rho_, v)));
             }
             // r.h.s. of the W system                                                                     :326-353
@@ -221,9 +235,13 @@ struct Solver {
 #pragma unroll 1
             for (int j = 0; j < n; ++j) {
                 real r = real(0);
+#if SPCIES_TERMINAL == 1
+#pragma unroll 1
+                for (int i = 0; i < n; ++i) r = A::add(r, A::mul((real)C->T_rho_i[j][i], s.ld(OFF_Z + ZN + i)));      // Hi_N z_N   :373-381
+#endif
 #pragma unroll 1
                 for (int i = 0; i < nm; ++i) r = A::sub(r, A::mul(A::mul(ab(j, i), hi(i)), s.ld(OFF_Z + el(N - 2, i))));
-                set_mu(N - 1, j, A::sub(r, s.ld(OFF_XR + j)));
+                set_mu(N - 1, j, LAX ? r : A::sub(r, s.ld(OFF_XR + j)));
             }
             // forward substitution                                                                       :358-388
 #pragma unroll 1
@@ -271,11 +289,25 @@ struct Solver {
                     for (int i = 0; i < n; ++i) z = A::add(z, A::mul(ab(i, j), mu(l + 1, i)));
                     s.st(OFF_Z + el(l, j), A::mul(-hi(j), z));
                 }
+#if SPCIES_TERMINAL == 1
+            {   // z_N = -Hi_N (z_N - mu_{N-1})                                                            code_laxMPC_ADMM_C.c:476-485
+                real aux[n];
+#pragma unroll
+                for (int j = 0; j < n; ++j) aux[j] = A::sub(s.ld(OFF_Z + ZN + j), mu(N - 1, j));
+#pragma unroll 1
+                for (int j = 0; j < n; ++j) {
+                    real z = real(0);
+#pragma unroll
+                    for (int i = 0; i < n; ++i) z = A::sub(z, A::mul((real)C->T_rho_i[j][i], aux[i]));
+                    s.st(OFF_Z + ZN + j, z);
+                }
+            }
+#endif
             // v, lambda, residuals                                                                       :449-524
             bool over = false;
 #pragma unroll 4
             for (int e = 0; e < ZLEN; ++e) {
-                const int c = e < m ? n + e : (e - m) % nm;
+                const int c = e < m ? n + e : (e < ZN ? (e - m) % nm : e - ZN);
                 const real z = s.ld(OFF_Z + e), lam = s.ld(OFF_LAM + e);
                 const real v = clip(A::add(z, A::mul(rhoi_, lam)), s.ld(OFF_LB + c), s.ld(OFF_UB + c));
                 s.st(OFF_V + e, v);

@@ -1,4 +1,4 @@
-// MPC_FISTA_tv.cuh -- batched laxMPC FISTA solver with a *per-instance* model (options.time_varying, `#define TIME_VARYING 1`),
+// MPC_FISTA_tv.cuh -- batched laxMPC (SPCIES_TERMINAL == 1) / equMPC (== 0) FISTA solver with a *per-instance* model (options.time_varying, `#define TIME_VARYING 1`),
 // hand-written for sm_100a.  Every instance brings its own A, B (column-major, as MATLAB passes them), diagonal Q, R and bounds:
 // the "one shared model" of the other kernels becomes "a model per instance", and the factorisation that the generator does off
 // line for a fixed model runs on the device, once per instance:
@@ -169,8 +169,13 @@ struct Solver {
                            [&](int i, real v) { return A::add(v, s.ld(QI + i)); });
                 alpha_block(h);
             }
+#if SPCIES_TERMINAL
             beta_block(N - 1, true, [&](int i, int j) { return A::add(s.ld(AQ + i * n + j), s.ld(BR + i * n + j)); },
                        [&](int i, real v) { return A::sub(v, C->Ti[i]); });                 // Ti is stored negated   :250-252
+#else
+            beta_block(N - 1, true, [&](int i, int j) { return A::add(s.ld(AQ + i * n + j), s.ld(BR + i * n + j)); },
+                       [&](int, real v) { return v; });                                     // code_equMPC_FISTA_C.c:236-254
+#endif
             // Q, R <- -Q, -R                                                                               :264-270
 #pragma unroll
             for (int i = 0; i < n; ++i) s.st(OFF_Q + i, -s.ld(OFF_Q + i));
@@ -184,7 +189,11 @@ struct Solver {
                 for (int i = 0; i < n; ++i) b = A::sub(b, A::mul(ab(j, i), x0[i]));
                 s.st(OFF_B + j, b);
                 s.st(OFF_QV + j, A::mul(s.ld(OFF_Q + j), xr[j]));
+#if SPCIES_TERMINAL
                 s.st(OFF_QT + j, A::mul(C->T[j], xr[j]));
+#else
+                s.st(OFF_QT + j, xr[j]);                       // equMPC: the terminal state is the reference   code_equMPC_FISTA_C.c:549
+#endif
             }
 #pragma unroll
             for (int j = 0; j < m; ++j) s.st(OFF_QV + n + j, A::mul(s.ld(OFF_R + j), ur[j]));
@@ -224,12 +233,14 @@ struct Solver {
                     v = A::mul(v, s.ld(OFF_QRI + j));
                     s.st(OFF_Z + l * nm + j, clip(v, s.ld(OFF_LB + j), s.ld(OFF_UB + j)));
                 }
+#if SPCIES_TERMINAL
 #pragma unroll
             for (int j = 0; j < n; ++j) {
                 real v = A::add(s.ld(OFF_QT + j), s.ld(off_lam + (N - 1) * n + j));
                 v = A::mul(v, C->Ti[j]);
                 s.st(OFF_ZN + j, clip(v, s.ld(OFF_LB + j), s.ld(OFF_UB + j)));
             }
+#endif
         }
         // residual -> d_lambda                                                                             :546-574
         __device__ void residual() {
@@ -244,7 +255,7 @@ struct Solver {
             for (int l = 1; l < N; ++l)
 #pragma unroll 1
                 for (int j = 0; j < n; ++j) {
-                    real v = l < N - 1 ? s.ld(OFF_Z + l * nm + j) : s.ld(OFF_ZN + j);
+                    real v = l < N - 1 ? s.ld(OFF_Z + l * nm + j) : (SPCIES_TERMINAL ? s.ld(OFF_ZN + j) : s.ld(OFF_QT + j));   // z_N | xr
 #pragma unroll
                     for (int i = 0; i < nm; ++i) v = A::sub(v, A::mul(ab(j, i), s.ld(OFF_Z + (l - 1) * nm + i)));
                     s.st(OFF_DL + l * n + j, v);
@@ -313,7 +324,9 @@ struct Solver {
                 int c = 0;
                 for (int j = 0; j < m; ++j) o[c++] = (double)s.ld(OFF_Z0 + j);
                 for (int e = 0; e < (N - 1) * nm; ++e) o[c++] = (double)s.ld(OFF_Z + e);
+#if SPCIES_TERMINAL
                 for (int j = 0; j < n; ++j) o[c++] = (double)s.ld(OFF_ZN + j);
+#endif
                 for (int e = 0; e < N * n; ++e) o[c++] = (double)s.ld(OFF_Y + e);
                 for (; c < (int)(sizeof(SPCIES_SOL_T) / sizeof(double)); ++c) o[c] = 0.0;
             }

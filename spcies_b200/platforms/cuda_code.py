@@ -53,7 +53,9 @@ KERNELS = {
 # solvers generated with options.time_varying (per-instance model, factorisation on the device)
 KERNELS_TV = {
     'laxMPC_FISTA': ('MPC_FISTA_tv.cuh', {'SPCIES_TERMINAL': 1}),
+    'equMPC_FISTA': ('MPC_FISTA_tv.cuh', {'SPCIES_TERMINAL': 0}),
     'equMPC_ADMM': ('MPC_ADMM_tv.cuh', {'SPCIES_TERMINAL': 0}),
+    'laxMPC_ADMM': ('MPC_ADMM_tv.cuh', {'SPCIES_TERMINAL': 1}),
 }
 
 

@@ -20,7 +20,7 @@ def _ref(name):
 TV = {'TV_laxMPC_FISTA': 'C2_laxMPC_FISTA', 'TV_equMPC_ADMM': 'C3_equMPC_ADMM'}     # time-varying solver -> its constant-model twin
 
 
-@pytest.mark.parametrize('name', list(TV))
+@pytest.mark.parametrize('name', list(TV) + ['TV_equMPC_FISTA', 'TV_laxMPC_ADMM'])
 def test_time_varying_batch_exact_and_fast(name):
     sol, spec, cfg = prebuilt.get(name)
     assert sol.tv

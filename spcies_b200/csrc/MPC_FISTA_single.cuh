@@ -8,11 +8,13 @@
 // [A B] (x_l, u_l)), z = clip(Hd o (q + E' y)) (:471-539), r = b + E z (:546-574), lambda+ = y + W^-1 r (:577-651, :364-369),
 // y+ = lambda+ + beta_k (lambda+ - lambda) (:372-385), the images v = E' y and mu = E' lambda obey
 //     mu+ = v + g + P z,   v+ = mu+ + beta_k (mu+ - mu),   z+ = clip(Hd o (q + v+)),      P = E' W^-1 E,  g = E' W^-1 b,
-// i.e. per iteration one dense |z| x |z| product with the shared vector z followed by component-wise work: one thread per row of P
-// (the row in registers, z read from shared memory with warp-uniform 128-bit loads = one wavefront each, no shuffles: the shared-
-// memory / shuffle pipe is what bounds a one-CTA iteration -- four threads per row cost 400 wavefronts + 80 shuffles = 1080 cycles
-// per iteration, tools/probes/lat_probe.cu), the residual rows (<= nm + 1 terms) in two more warps, and one __syncthreads_or that
-// carries the exit decision (:337-361) and the new z (double buffered).  P and g are formed on the host in extended precision
+// i.e. per iteration one dense |z| x |z| product with the shared vector z followed by component-wise work.  A pair of threads owns
+// two rows of P: each has both rows' coefficients for half of the columns in registers, reads its half of z from shared memory
+// (128-bit loads, two addresses per warp) and exchanges one partial sum with its partner, then updates its own row.  The shared-
+// memory / shuffle pipe is what bounds a one-CTA iteration: a load fills 4 bytes per lane and cycle whatever its width and
+// uniformity (measured per iteration: four threads per row with two butterfly steps 1080 cycles, one thread per row reading all
+// of z 800, this scheme 745; tools/probes/lat_probe.cu, tools/latency_probe.py).  The residual rows (<= nm + 1 terms) run in two
+// more warps, and one __syncthreads_or carries the exit decision (:337-361) and the new z (double buffered).  P and g are formed on the host in extended precision
 // from Alpha / Beta; beta_k comes from a table (the t-sequence does not depend on the instance).
 // FAST arithmetic only (the sums run in a different order than the reference's); used for host-buffer batches
 // of at most 64 instances (spcies_host.cuh: run_small), one CTA each; the inputs of up to 4 instances travel as kernel arguments
@@ -25,14 +27,15 @@
 
 constexpr int SG_ROWS = N * n;                                   // dual variables
 constexpr int SG_ZLEN = TERMINAL ? N * nm : N * nm - n;          // primal variables
-constexpr int SG_ZPAD = (SG_ZLEN + 3) / 4 * 4;
+constexpr int SG_ZPAD = (SG_ZLEN + 7) / 8 * 8;
+constexpr int SG_H = SG_ZPAD / 2;                                 // columns per thread: two rows x half the columns
 constexpr int SG_MR = (SG_ZLEN + 31) / 32 * 32;                  // threads [0, SG_MR): one row of P each
 constexpr int SG_RR = (SG_ROWS + 31) / 32 * 32;                  // threads [SG_MR, SG_MR + SG_RR): one residual row each
 constexpr int SG_BLOCK = SG_MR + SG_RR;
 constexpr int SG_NZ2 = nm + 1;
 constexpr int SG_KTAB = k_max + 2;
 constexpr int SG_NARG = 4;                                       // instances whose inputs fit the kernel arguments
-constexpr bool HAS_SINGLE = SPCIES_FISTA_SINGLE != 0 && sizeof(real) == 8 && SG_BLOCK <= 1024 && SG_ZPAD <= 96 && SG_KTAB <= 16384;
+constexpr bool HAS_SINGLE = SPCIES_FISTA_SINGLE != 0 && sizeof(real) == 8 && SG_BLOCK <= 1024 && SG_ZPAD <= 96 && SG_MR % 2 == 0 && SG_KTAB <= 16384;
 
 struct SingleArgs {
     int count;                                                   // 0: read the inputs through BatchIO
@@ -41,7 +44,7 @@ struct SingleArgs {
 
 struct alignas(16) SingleTables {
     // [term][thread]: coalesced loads into registers at the start of the kernel
-    double P[SG_ZPAD][SG_MR];              // thread e: row e of P
+    double P[SG_ZPAD][SG_MR];              // P[col][row]; thread e works on rows (e & ~1, e | 1), columns [(e & 1) SG_H, .. + SG_H)
     double Hd[SG_MR], cq[SG_MR];           // q_e = cq_e ref[qsrc_e], ref = (xr, ur)   (Q, R, T stored negated)
     double LB[SG_MR], UB[SG_MR];
     double cg[2 * n][SG_MR];               // g_e = sum_j cg[j] x0_j + sum_j cg[n + j] xr_j
@@ -224,7 +227,7 @@ static inline void fill_single_tables(const PrimalForm &F, SingleTables &T) {
 
 // ---- per-thread coefficients (registers), loaded once per kernel
 struct SingleLane {
-    double w[SG_ZPAD];          // mat: row e of P;  else: the first SG_NZ2 entries hold the residual row's terms
+    double w[SG_ZPAD];          // mat: half rows of the pair (w[j], w[SG_H + j]);  else: the first SG_NZ2 entries hold the residual row's terms
     int i2[SG_NZ2];
     double hd, lb, ub;
     int e;
@@ -236,7 +239,10 @@ struct SingleLane {
         hd = lb = ub = 0.0;
         if (mat) {
 #pragma unroll
-            for (int j = 0; j < SG_ZPAD; ++j) w[j] = T->P[j][e];
+            for (int j = 0; j < SG_H; ++j) {
+                w[j] = T->P[(e & 1) * SG_H + j][e & ~1];
+                w[SG_H + j] = T->P[(e & 1) * SG_H + j][e | 1];
+            }
             hd = T->Hd[e];
             lb = T->LB[e];
             ub = T->UB[e];
@@ -280,28 +286,25 @@ __device__ __forceinline__ void single_solve(const SingleTables *T, const Single
         bool over = false;
         if (L.mat) {
             const double bk = T->beta[k];
-            const double2 *z2 = reinterpret_cast<const double2 *>(zc);
-            double a[8] = {ce, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+            // rows (e & ~1, e | 1) x this thread's half of the columns; the partner thread has the other half
+            const double2 *z2 = reinterpret_cast<const double2 *>(zc + (e & 1) * SG_H);
+            double a[4] = {0.0, 0.0, 0.0, 0.0}, b[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-            for (int j = 0; j + 7 < SG_ZPAD; j += 8) {
-                const double2 p0 = z2[j / 2], p1 = z2[j / 2 + 1], p2 = z2[j / 2 + 2], p3 = z2[j / 2 + 3];
+            for (int j = 0; j < SG_H; j += 4) {
+                const double2 p0 = z2[j / 2], p1 = z2[j / 2 + 1];
                 a[0] = fma(L.w[j], p0.x, a[0]);
                 a[1] = fma(L.w[j + 1], p0.y, a[1]);
                 a[2] = fma(L.w[j + 2], p1.x, a[2]);
                 a[3] = fma(L.w[j + 3], p1.y, a[3]);
-                a[4] = fma(L.w[j + 4], p2.x, a[4]);
-                a[5] = fma(L.w[j + 5], p2.y, a[5]);
-                a[6] = fma(L.w[j + 6], p3.x, a[6]);
-                a[7] = fma(L.w[j + 7], p3.y, a[7]);
+                b[0] = fma(L.w[SG_H + j], p0.x, b[0]);
+                b[1] = fma(L.w[SG_H + j + 1], p0.y, b[1]);
+                b[2] = fma(L.w[SG_H + j + 2], p1.x, b[2]);
+                b[3] = fma(L.w[SG_H + j + 3], p1.y, b[3]);
             }
-            if (SG_ZPAD % 8) {
-                const double2 p0 = z2[SG_ZPAD / 2 - 2], p1 = z2[SG_ZPAD / 2 - 1];
-                a[0] = fma(L.w[SG_ZPAD - 4], p0.x, a[0]);
-                a[1] = fma(L.w[SG_ZPAD - 3], p0.y, a[1]);
-                a[2] = fma(L.w[SG_ZPAD - 2], p1.x, a[2]);
-                a[3] = fma(L.w[SG_ZPAD - 1], p1.y, a[3]);
-            }
-            const double d = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+            double d0 = (a[0] + a[1]) + (a[2] + a[3]), d1 = (b[0] + b[1]) + (b[2] + b[3]);
+            // each thread keeps the sum of its own row (row e): send the partner's partial sum, receive mine
+            const double mine = (e & 1) ? d1 : d0, theirs = (e & 1) ? d0 : d1;
+            const double d = ce + mine + __shfl_xor_sync(0xffffffffu, theirs, 1);
             const double mnew = v + d;                               // E' (y + W^-1 r)
             v = k == 0 ? mnew : fma(bk, mnew - mu, mnew);            // :311-320 | :372-385 (beta_1 = 0)
             mu = mnew;

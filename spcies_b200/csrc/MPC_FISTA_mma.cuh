@@ -36,6 +36,12 @@
 #define SPCIES_FISTA_MMA_PRESCALE 1  // 1: fold the QRi / Ti scalings of z into [A B]' and q (one FP64 operation less per component of z;
                                      // the constants are rounded once more: same measured accuracy, tools/diag_equ.py)
 #endif
+#ifndef SPCIES_FISTA_MMA_INT_CLIP
+#define SPCIES_FISTA_MMA_INT_CLIP 0      // clip with integer compares on order-preserving keys of the doubles (measured)
+#endif
+#ifndef SPCIES_FISTA_MMA_INT_TEST
+#define SPCIES_FISTA_MMA_INT_TEST 0      // exit test with integer compares (tools/engine_variants.py: measured)
+#endif
 #ifndef SPCIES_FISTA_MMA_MERGE
 #define SPCIES_FISTA_MMA_MERGE 1     // 1: permuted component layout that lets two n-vector products share a k-step (5 <= nn_ <= 6)
 #endif
@@ -84,6 +90,24 @@ __host__ __device__ constexpr int xo_at(int c) {
         for (int e = 4; e < n; ++e)
             if (col_dup(e) == c) return e;
     return -1;
+}
+
+// order-preserving integer key of a double (sign-magnitude -> two's complement): a > b  <=>  key(a) > key(b) for non-NaN values
+__device__ __forceinline__ long long dkey(double x) {
+    const long long b = __double_as_longlong(x);
+    return b ^ ((b >> 63) & 0x7fffffffffffffffLL);
+}
+// clip() of spcies_common.cuh with the two compares on the integer pipe
+__device__ __forceinline__ double clip_mma(double v, double lo, double hi) {
+#if SPCIES_FISTA_MMA_INT_CLIP
+    const long long kv = dkey(v), kl = dkey(lo), kh = dkey(hi);
+    const bool above = kv > kl;
+    const double t = above ? v : lo;
+    const long long kt = above ? kv : kl;
+    return kt > kh ? hi : t;
+#else
+    return clip(v, lo, hi);
+#endif
 }
 
 struct alignas(16) MmaTables {
@@ -382,7 +406,7 @@ __global__ void __launch_bounds__(BLOCK, 1) fista_mma_kernel(const BatchIO io, c
         }
 #pragma unroll
         for (int i = 0; i < 2; ++i)                                                        // u_0; lo0 = hi0 = x0 on the state part
-            zz[0][i] = clip(PRESCALE ? zz[0][i] : zz[0][i] * qri[i], lo0[i], hi0[i]);
+            zz[0][i] = clip_mma(PRESCALE ? zz[0][i] : zz[0][i] * qri[i], lo0[i], hi0[i]);
         u0v[0] = zz[0][0];
         u0v[1] = zz[0][1];
 #pragma unroll
@@ -391,14 +415,14 @@ __global__ void __launch_bounds__(BLOCK, 1) fista_mma_kernel(const BatchIO io, c
             for (int i = 0; i < 2; ++i) {
                 double lo, hi;
                 bnd(l + 1, i, lo, hi);
-                zz[l + 1][i] = clip(PRESCALE ? fma(qriy[i], y[l][i], zz[l + 1][i]) : (zz[l + 1][i] + y[l][i]) * qri[i], lo, hi);   // z_l  :494-519
+                zz[l + 1][i] = clip_mma(PRESCALE ? fma(qriy[i], y[l][i], zz[l + 1][i]) : (zz[l + 1][i] + y[l][i]) * qri[i], lo, hi);   // z_l  :494-519
             }
 #if SPCIES_TERMINAL
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
             double lo, hi;
             bnd(N, i, lo, hi);
-            zz[N][i] = clip(PRESCALE ? fma(ti[i], y[N - 1][i], qT[i]) : (qT[i] + y[N - 1][i]) * ti[i], lo, hi);   // z_N  :522-537
+            zz[N][i] = clip_mma(PRESCALE ? fma(ti[i], y[N - 1][i], qT[i]) : (qT[i] + y[N - 1][i]) * ti[i], lo, hi);   // z_N  :522-537
         }
 #else
         zz[N][0] = qT[0];                                                                   // xr   code_equMPC_FISTA_C.c:549
@@ -413,8 +437,20 @@ __global__ void __launch_bounds__(BLOCK, 1) fista_mma_kernel(const BatchIO io, c
 #pragma unroll
             for (int l = 0; l < N; ++l) dmma(r[l][0], r[l][1], zz[l][1], nab.y, e[l][0], e[l][1]);
         }
+#if SPCIES_FISTA_MMA_INT_TEST
+        {   // |r| > tol on the integer pipe (the FP64 datapath is the bound of this kernel): for non-negative doubles the bit patterns
+            // order like the values, so |r| > tol  <=>  (bits(r) & ~sign) > bits(tol); a NaN residual counts as "not converged"
+            const unsigned long long tb0 = (unsigned long long)__double_as_longlong(tolv[0]), tb1 = (unsigned long long)__double_as_longlong(tolv[1]);
+            constexpr unsigned long long ABS = 0x7fffffffffffffffULL;
+#pragma unroll
+            for (int l = 0; l < N; ++l)
+                over = over || (((unsigned long long)__double_as_longlong(r[l][0]) & ABS) > tb0) ||
+                       (((unsigned long long)__double_as_longlong(r[l][1]) & ABS) > tb1);
+        }
+#else
 #pragma unroll
         for (int l = 0; l < N; ++l) over = over || (fabs(r[l][0]) > tolv[0]) || (fabs(r[l][1]) > tolv[1]);
+#endif
         // forward step: mu_l = Linv_l r_l - F_l mu_{l-1}   [plain layout: and w_l = Uinv_l mu_l, stored in w]
         if constexpr (MERGE) {
             // w[l] keeps mu_l.  Per stage: e_l = Linv r (full k-step, issued ahead), f = e_l - F mu_{l-1} (full k-step),

@@ -86,15 +86,13 @@ template <class E> struct Plan {
     static constexpr size_t FIXED = SMALL_BYTES + CTRL_BYTES;
     // resident table: at least 4 groups must fit beside it
     static constexpr bool RESIDENT = FIXED + FRAG_BYTES + 4 * GROUP_BYTES <= SMEM_LIMIT && STAGES_PER_ITER <= 96;
-    static constexpr int NSTAGE_MIN = RESIDENT ? STAGES_PER_ITER : 8;
-    static constexpr size_t RING_MIN = (size_t)NSTAGE_MIN * STAGE_BYTES;
-    static constexpr int GROUPS_RAW = FIXED + RING_MIN >= SMEM_LIMIT ? 0 : (int)((SMEM_LIMIT - FIXED - RING_MIN) / GROUP_BYTES);
+    // a streamed table goes through a ring of 8 stages (a deeper ring was measured on HMPC N = 50: 11 stages, no gain -- the
+    // stream is not bound by the bytes in flight); Ctrl::empty has one barrier per ring slot
+    static constexpr int NSTAGE = RESIDENT ? STAGES_PER_ITER : 8;
+    static constexpr size_t RING_BYTES = (size_t)NSTAGE * STAGE_BYTES;
+    static constexpr int GROUPS_RAW = FIXED + RING_BYTES >= SMEM_LIMIT ? 0 : (int)((SMEM_LIMIT - FIXED - RING_BYTES) / GROUP_BYTES);
     static constexpr int GROUPS_MAX = 8 / TEAM;
     static constexpr int GROUPS = GROUPS_RAW > GROUPS_MAX ? GROUPS_MAX : GROUPS_RAW;
-    // a streamed table: the shared memory the groups leave over deepens the ring (bytes in flight against the L2 latency), up to 16 stages
-    static constexpr int NSTAGE_FIT = (int)((SMEM_LIMIT - FIXED - (size_t)GROUPS * GROUP_BYTES) / STAGE_BYTES);
-    static constexpr int NSTAGE = RESIDENT ? STAGES_PER_ITER : (NSTAGE_FIT > 16 ? 16 : (NSTAGE_FIT < 8 ? 8 : NSTAGE_FIT));
-    static constexpr size_t RING_BYTES = (size_t)NSTAGE * STAGE_BYTES;
     static constexpr int CONSUMER_WARPS = GROUPS * TEAM;
     static constexpr int BLOCK = (CONSUMER_WARPS + 1) * 32;          // + the producer warp
     static constexpr int IPB = GROUPS * 8;
@@ -147,6 +145,7 @@ struct Ctrl {                       // first bytes of the dynamic shared memory
     unsigned over[8][2];            // team mailbox: exit-test ballots
 };
 static_assert(sizeof(Ctrl) <= 1536, "Ctrl");
+static_assert(sizeof(((Ctrl *)nullptr)->empty) / sizeof(uint64_t) == 8, "one `empty` barrier per slot of the streaming ring");
 
 // ---- host: dense map -> fragment table in consumption order --------------------------------------------------------------------
 template <class E> static inline void fill_fragments(const long double *F, double2 *frag) {

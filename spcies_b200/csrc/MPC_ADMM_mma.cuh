@@ -26,7 +26,7 @@
 #define SPCIES_ADMM_MMA 1
 #endif
 #ifndef SPCIES_ADMM_MMA_BLOCK
-#define SPCIES_ADMM_MMA_BLOCK 256
+#define SPCIES_ADMM_MMA_BLOCK 0          // 0: as many warps as the iterates leave room for, 8 .. 12 (below)
 #endif
 
 #if defined(SCALAR_RHO) && !defined(VAR_BOUNDS)
@@ -35,8 +35,6 @@
 #define SPCIES_ADMM_MMA_ELIGIBLE 0
 #endif
 
-constexpr int MMA_BLOCK = SPCIES_ADMM_MMA_BLOCK;
-constexpr int MMA_IPB = MMA_BLOCK / 4;
 constexpr bool MMA_SHAPE_OK = n >= 5 && n <= 6 && nm <= 8 && N >= 3;
 constexpr int MMA_NBLK = N + (HAS_TN ? 1 : 0);   // blocks of v / lambda: u_0, stages 0..N-2 [, the terminal state of laxMPC]
 constexpr size_t MMA_STATE_PER_WARP = (size_t)2 * MMA_NBLK * 32 * sizeof(double2);
@@ -62,6 +60,12 @@ struct alignas(16) MmaTables {
 constexpr size_t MMA_BYTES = (sizeof(MmaTables) + 15) / 16 * 16;
 constexpr size_t CONSTS_BYTES_ = (sizeof(spcies_consts) + 15) / 16 * 16;
 constexpr size_t MMA_OFFSET = CONSTS_BYTES_;
+// Warps per SM: the kernel needs 168 registers (12 warps) and 2 N tiles of iterates per warp; the recurrences are latency bound,
+// so every warp that fits helps (C3, N = 20: 9 warps 4.23 M solves/s against 4.16 M with 8; N = 10: 12 warps)
+constexpr int MMA_FIT = MMA_BYTES + 64 >= 227 * 1024 ? 0 : (int)((227 * 1024 - 64 - MMA_BYTES) / MMA_STATE_PER_WARP);
+constexpr int MMA_WARPS = MMA_FIT >= 12 ? 12 : (MMA_FIT >= 8 ? MMA_FIT : 8);
+constexpr int MMA_BLOCK = SPCIES_ADMM_MMA_BLOCK > 0 ? SPCIES_ADMM_MMA_BLOCK : 32 * MMA_WARPS;
+constexpr int MMA_IPB = MMA_BLOCK / 4;
 constexpr size_t MMA_SMEM = MMA_BYTES + (MMA_BLOCK / 32) * MMA_STATE_PER_WARP;
 constexpr bool HAS_MMA = SPCIES_ADMM_MMA != 0 && MMA_SHAPE_OK && sizeof(SPCIES_REAL) == 8 && MMA_SMEM <= 227 * 1024 - 64;
 

@@ -29,7 +29,14 @@
 #endif
 
 constexpr bool MMA_SHAPE_OK = n >= 5 && n <= 6 && nm <= 8 && N >= 3;
-constexpr int PF = 4;                                             // prefetch distance (stages) of the recurrence fragments
+#ifndef SPCIES_EADMM_PF
+#define SPCIES_EADMM_PF 4
+#endif
+#ifndef SPCIES_EADMM_P1_UNROLL
+#define SPCIES_EADMM_P1_UNROLL 4       // measured on C5b (256 Ki instances): 1.694 / 1.726 / 1.648 M solves/s at 2 / 4 / 5; PF 2 / 4 / 6: 1.678 / 1.694 / 1.704
+#endif
+constexpr int P1U = SPCIES_EADMM_P1_UNROLL;                        // unroll factor of the (stage-parallel) P1 loop
+constexpr int PF = SPCIES_EADMM_PF;                               // prefetch distance (stages) of the recurrence fragments
 constexpr int MMA_NBLK = 2 * N + 4;                               // z3[N+1], lambda[N+3]   (z1 recomputed, mu' streamed through L2)
 constexpr int BLK_Z3 = 0, BLK_LAM = N + 1;
 constexpr size_t MMA_STATE_PER_WARP = (size_t)MMA_NBLK * 32 * sizeof(double2);
@@ -223,7 +230,7 @@ __global__ void __launch_bounds__(MMA_BLOCK, 1) eadmm_mma_kernel(const BatchIO i
         }
         // ---------- P1 for l = 0..N-1 fused with the q2 accumulation                      :97-110, :137-141
         {
-#pragma unroll 2
+#pragma unroll P1U
             for (int l = 0; l < N; ++l) {
                 const double2 z3l = LD(BLK_Z3 + l), l1 = LD(BLK_LAM + l + 1), rl = ROW(T->rho, l);
                 const double2 v = z1_of(l, z3l, l1);

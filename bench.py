@@ -627,16 +627,19 @@ def main():
         ref1.solve_batch(rep(stt['x']), rep(stt['xr']), rep(stt['ur']), threads=1, **({'r': np.full(nrep, rr)} if sol.has_r else {}))
         c_us = (time.perf_counter() - t0) / nrep * 1e6
         # the same symbol called from plain C (harness/main_batch.c, the reference's examples/cl_in_C pattern): no ctypes overhead
-        c_p50 = None
+        c_p50, c_p50_launch = None, None
         exe = os.path.join(ROOT, 'harness', 'main_batch')
         if args.config == 'C2' and os.path.exists(exe):
             try:
                 out = subprocess.run([exe, '64', '0'], capture_output=True, text=True, timeout=120).stdout
                 c_p50 = float(out.split('p50 latency =')[1].split('us')[0])
+                out = subprocess.run([exe, '64', '0'], capture_output=True, text=True, timeout=120,
+                                     env=dict(os.environ, SPCIES_CUDA_SERVER_LINGER_US='0')).stdout
+                c_p50_launch = float(out.split('p50 latency =')[1].split('us')[0])
             except Exception:
-                c_p50 = None
+                pass
         single = {'p50_us': c_p50 if c_p50 is not None else g50, 'p50_us_ctypes': g50, 'p99_us_ctypes': g99, 'k': int(ks),
-                  'cpu_reference_us': c_us,
+                  'cpu_reference_us': c_us, 'p50_us_one_launch_per_call': c_p50_launch,
                   'how': 'single-instance symbol: p50 of 200 back-to-back calls from plain C (harness/main_batch) when available, p50 / p99 '
                          'of 1000 calls through ctypes; FISTA solvers: served by the lingering one-CTA kernel through its mapped-memory '
                          'mailbox (SPCIES_CUDA_SERVER_LINGER_US, default 200; 0 = one launch per call), others: a batch of one; '

@@ -41,6 +41,13 @@
 namespace spcies {
 namespace dense {
 
+// Lanes of the producer warp that feed the ring.  One lane's loop (wait for a free slot, expect_tx, bulk copy: a chain of
+// shared-memory / mbarrier round trips, ~400 cycles per 4 KB stage) was what bounded the streamed engines, not L2 and not the ring
+// depth: HMPC N = 50, 16 Ki instances: 219.6 ms with 1 lane, 147.9 ms with 2, 154.4 ms with 4 (tools/engine_variants.py)
+#ifndef SPCIES_DENSE_PRODUCER_LANES
+#define SPCIES_DENSE_PRODUCER_LANES 2
+#endif
+constexpr int PRODUCER_LANES = SPCIES_DENSE_PRODUCER_LANES;       // 1, 2, 4 or 8: divides the 8 slots of the ring
 constexpr size_t SMEM_LIMIT = 227 * 1024 - 256;
 constexpr int TILE_BYTES = 32 * sizeof(double2);   // 512
 
@@ -200,38 +207,46 @@ template <class E> __global__ void __launch_bounds__(Plan<E>::BLOCK, 1) dense_mm
 
     // =============================================== producer warp ===============================================
     if (warp == P::CONSUMER_WARPS) {
-        if (lane == 0) {
-            if (P::RESIDENT) {
+        if (P::RESIDENT) {
+            if (lane == 0) {
                 for (int s = 0; s < P::NSTAGE; ++s) {
                     mbar_expect_tx(&ctrl->full[s], (unsigned)P::STAGE_BYTES);
                     bulk_g2s(ring + (size_t)s * P::STAGE_BYTES, g_frag + (size_t)s * P::STAGE_BYTES, (unsigned)P::STAGE_BYTES, &ctrl->full[s]);
                 }
                 for (int s = 0; s < P::NSTAGE; ++s) mbar_wait(&ctrl->full[s], 0);     // never leave with copies in flight
-            } else {
-                int issued = 0, slot = 0, idx = r0 * P::NCH * TEAM;     // idx: stage of the table (the stream starts at round r0)
-                unsigned par = 1;                      // parity of the `empty` phase to wait for (1: passes on a fresh barrier)
-                bool stopped = false;
-                for (;;) {
-                    while (!mbar_try_wait(&ctrl->empty[slot], par)) {
-                        if (*(volatile int *)&ctrl->stop) {
-                            stopped = true;
-                            break;
-                        }
-                    }
-                    if (stopped || *(volatile int *)&ctrl->stop) break;
-                    mbar_expect_tx(&ctrl->full[slot], (unsigned)P::STAGE_BYTES);
-                    bulk_g2s(ring + (size_t)slot * P::STAGE_BYTES, g_frag + (size_t)idx * P::STAGE_BYTES, (unsigned)P::STAGE_BYTES,
-                             &ctrl->full[slot]);
-                    ++issued;
-                    if (++idx == P::STAGES_PER_ITER) idx = 0;
-                    if (++slot == P::NSTAGE) {
-                        slot = 0;
-                        par ^= 1u;
+            }
+        } else if (lane < PRODUCER_LANES) {
+            // lane l feeds the ring slots l, l + PRODUCER_LANES, ...: the wait for a free slot, the expect_tx and the copy of a stage are
+            // a chain of shared-memory round trips, several lanes keep several of them in flight
+            int issued = 0, slot = lane, idx = (r0 * P::NCH * TEAM + lane) % P::STAGES_PER_ITER;   // idx: stage of the table (the stream starts at round r0)
+            unsigned par = 1;                          // parity of the `empty` phase to wait for (1: passes on a fresh barrier)
+            bool stopped = false;
+            for (;;) {
+                while (!mbar_try_wait(&ctrl->empty[slot], par)) {
+                    if (*(volatile int *)&ctrl->stop) {
+                        stopped = true;
+                        break;
                     }
                 }
-                // drain: the stages issued beyond what the consumers took must land before the CTA may exit
-                const int consumed = *(volatile int *)&ctrl->final_stages;
-                for (int g = consumed; g < issued; ++g) mbar_wait(&ctrl->full[g % P::NSTAGE], (unsigned)((g / P::NSTAGE) & 1));
+                if (stopped || *(volatile int *)&ctrl->stop) break;
+                mbar_expect_tx(&ctrl->full[slot], (unsigned)P::STAGE_BYTES);
+                bulk_g2s(ring + (size_t)slot * P::STAGE_BYTES, g_frag + (size_t)idx * P::STAGE_BYTES, (unsigned)P::STAGE_BYTES,
+                         &ctrl->full[slot]);
+                ++issued;
+                idx += PRODUCER_LANES;
+                if (idx >= P::STAGES_PER_ITER) idx -= P::STAGES_PER_ITER;
+                slot += PRODUCER_LANES;
+                if (slot >= P::NSTAGE) {
+                    slot -= P::NSTAGE;
+                    par ^= 1u;
+                }
+            }
+            // drain: the stages issued beyond what the consumers took must land before the CTA may exit
+            const int consumed = *(volatile int *)&ctrl->final_stages;
+            int q = consumed > lane ? (consumed - lane + PRODUCER_LANES - 1) / PRODUCER_LANES : 0;
+            for (; q < issued; ++q) {
+                const int g = lane + PRODUCER_LANES * q;
+                mbar_wait(&ctrl->full[g % P::NSTAGE], (unsigned)((g / P::NSTAGE) & 1));
             }
         }
         return;

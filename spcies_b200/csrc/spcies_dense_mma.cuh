@@ -41,13 +41,21 @@
 namespace spcies {
 namespace dense {
 
-// Lanes of the producer warp that feed the ring.  One lane's loop (wait for a free slot, expect_tx, bulk copy: a chain of
-// shared-memory / mbarrier round trips, ~400 cycles per 4 KB stage) was what bounded the streamed engines, not L2 and not the ring
-// depth: HMPC N = 50, 16 Ki instances: 219.6 ms with 1 lane, 147.9 ms with 2, 154.4 ms with 4 (tools/engine_variants.py)
+// Producers of the fragment stream: PRODUCER_WARPS warps x PRODUCER_LANES lanes, producer p feeding the ring slots p, p + P, ...
+// One thread's loop (wait for a free slot, expect_tx, bulk copy: a chain of shared-memory / mbarrier round trips, ~400 cycles per
+// 4 KB stage) was what bounded the streamed engines -- not L2, not the ring depth.  HMPC N = 50, 16 Ki instances
+// (tools/engine_variants.py): 1 thread 219.6 ms; 2 / 4 lanes of one warp 147.9 / 154.4 ms (the lanes' spin loops serialise);
+// 2 / 4 / 8 warps with one lane each 129.9 / 111.1 / 111.1 ms; 2 warps x 2 lanes 115.6 ms.  Four warps: the consumers' MMAs bound it.
 #ifndef SPCIES_DENSE_PRODUCER_LANES
-#define SPCIES_DENSE_PRODUCER_LANES 2
+#define SPCIES_DENSE_PRODUCER_LANES 1
 #endif
 constexpr int PRODUCER_LANES = SPCIES_DENSE_PRODUCER_LANES;       // 1, 2, 4 or 8: divides the 8 slots of the ring
+#ifndef SPCIES_DENSE_PRODUCER_WARPS
+#define SPCIES_DENSE_PRODUCER_WARPS 4
+#endif
+constexpr int PRODUCER_WARPS = SPCIES_DENSE_PRODUCER_WARPS;       // producers = warps x lanes, each feeding every (warps x lanes)-th slot
+constexpr int PRODUCERS = PRODUCER_WARPS * PRODUCER_LANES;
+static_assert(8 % PRODUCERS == 0, "the producers split the 8 slots of the ring evenly");
 constexpr size_t SMEM_LIMIT = 227 * 1024 - 256;
 constexpr int TILE_BYTES = 32 * sizeof(double2);   // 512
 
@@ -101,7 +109,7 @@ template <class E> struct Plan {
     static constexpr int GROUPS_MAX = 8 / TEAM;
     static constexpr int GROUPS = GROUPS_RAW > GROUPS_MAX ? GROUPS_MAX : GROUPS_RAW;
     static constexpr int CONSUMER_WARPS = GROUPS * TEAM;
-    static constexpr int BLOCK = (CONSUMER_WARPS + 1) * 32;          // + the producer warp
+    static constexpr int BLOCK = (CONSUMER_WARPS + PRODUCER_WARPS) * 32;   // + the producer warp(s)
     static constexpr int IPB = GROUPS * 8;
     static constexpr size_t SMEM = FIXED + RING_BYTES + (size_t)GROUPS * GROUP_BYTES;
     static constexpr size_t OFF_SMALL = BlobOffset<E>::value;        // blob: spcies_consts [| other tables] | Small | fragments
@@ -206,9 +214,10 @@ template <class E> __global__ void __launch_bounds__(Plan<E>::BLOCK, 1) dense_mm
     __syncthreads();
 
     // =============================================== producer warp ===============================================
-    if (warp == P::CONSUMER_WARPS) {
+    if (warp >= P::CONSUMER_WARPS) {
+        const int pid = (warp - P::CONSUMER_WARPS) * PRODUCER_LANES + lane;     // producer index of this lane
         if (P::RESIDENT) {
-            if (lane == 0) {
+            if (pid == 0 && lane == 0) {
                 for (int s = 0; s < P::NSTAGE; ++s) {
                     mbar_expect_tx(&ctrl->full[s], (unsigned)P::STAGE_BYTES);
                     bulk_g2s(ring + (size_t)s * P::STAGE_BYTES, g_frag + (size_t)s * P::STAGE_BYTES, (unsigned)P::STAGE_BYTES, &ctrl->full[s]);
@@ -218,7 +227,7 @@ template <class E> __global__ void __launch_bounds__(Plan<E>::BLOCK, 1) dense_mm
         } else if (lane < PRODUCER_LANES) {
             // lane l feeds the ring slots l, l + PRODUCER_LANES, ...: the wait for a free slot, the expect_tx and the copy of a stage are
             // a chain of shared-memory round trips, several lanes keep several of them in flight
-            int issued = 0, slot = lane, idx = (r0 * P::NCH * TEAM + lane) % P::STAGES_PER_ITER;   // idx: stage of the table (the stream starts at round r0)
+            int issued = 0, slot = pid, idx = (r0 * P::NCH * TEAM + pid) % P::STAGES_PER_ITER;   // idx: stage of the table (the stream starts at round r0)
             unsigned par = 1;                          // parity of the `empty` phase to wait for (1: passes on a fresh barrier)
             bool stopped = false;
             for (;;) {
@@ -233,9 +242,9 @@ template <class E> __global__ void __launch_bounds__(Plan<E>::BLOCK, 1) dense_mm
                 bulk_g2s(ring + (size_t)slot * P::STAGE_BYTES, g_frag + (size_t)idx * P::STAGE_BYTES, (unsigned)P::STAGE_BYTES,
                          &ctrl->full[slot]);
                 ++issued;
-                idx += PRODUCER_LANES;
+                idx += PRODUCERS;
                 if (idx >= P::STAGES_PER_ITER) idx -= P::STAGES_PER_ITER;
-                slot += PRODUCER_LANES;
+                slot += PRODUCERS;
                 if (slot >= P::NSTAGE) {
                     slot -= P::NSTAGE;
                     par ^= 1u;
@@ -243,9 +252,9 @@ template <class E> __global__ void __launch_bounds__(Plan<E>::BLOCK, 1) dense_mm
             }
             // drain: the stages issued beyond what the consumers took must land before the CTA may exit
             const int consumed = *(volatile int *)&ctrl->final_stages;
-            int q = consumed > lane ? (consumed - lane + PRODUCER_LANES - 1) / PRODUCER_LANES : 0;
+            int q = consumed > pid ? (consumed - pid + PRODUCERS - 1) / PRODUCERS : 0;
             for (; q < issued; ++q) {
-                const int g = lane + PRODUCER_LANES * q;
+                const int g = pid + PRODUCERS * q;
                 mbar_wait(&ctrl->full[g % P::NSTAGE], (unsigned)((g / P::NSTAGE) & 1));
             }
         }
